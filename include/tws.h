@@ -1,0 +1,204 @@
+/* tws.h — C ABI of libtws.so, the B200-native replacement for the simulation half of
+ * terrainwatersim's `Terrain` class (terrainwatersim/source/scene/Terrain.{h,cpp}) and
+ * the three compute shaders it dispatches (shader/flowUpdate.comp, flowApply.comp,
+ * waterBrush.comp).  The reference has no FFI layer: the boundary it offers is the
+ * public half of `Terrain` (Terrain.h:18-39,76-83) plus the GL textures the renderer
+ * samples (Terrain.cpp:288,323-330).  Each entry point below names the reference
+ * interface it replaces.  All arithmetic happens on the GPU (sm_100a); there is no CPU
+ * fallback: tws_create fails with TWS_ERR_CUDA when no usable device exists.
+ *
+ * Conventions: plain C types only; every call returns a tws_status (0 = OK, negative =
+ * error) and never throws or aborts; the message of the last failure on a sim is
+ * returned by tws_last_error.  A tws_sim is not re-entrant (the reference is single
+ * threaded, RenderWindow.cpp:103-108): the caller serialises calls on one sim.  Calls
+ * enqueue work on library-owned CUDA streams and return without synchronising, except
+ * tws_readback / tws_total_volume / tws_sync / tws_elapsed_ms.
+ *
+ * Grid layout seen through this ABI is the reference's: row-major, index x + y*width
+ * (Terrain.cpp:216), y = 0 the first row.  A sim may own only a STRIP of rows
+ * [row_begin,row_end) of a larger global grid (multi-GPU row decomposition, one
+ * process or thread per GPU); host buffers passed to upload/readback then hold the
+ * strip's own rows only.
+ */
+#ifndef TWS_H_
+#define TWS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TWS_ABI_VERSION 1
+
+typedef struct tws_sim tws_sim;
+
+typedef enum tws_status {
+  TWS_OK = 0,
+  TWS_ERR_INVALID = -1,     /* bad argument / precondition                        */
+  TWS_ERR_CUDA = -2,        /* CUDA runtime/driver failure, or no sm_100 device   */
+  TWS_ERR_NOMEM = -3,       /* device allocation failed                           */
+  TWS_ERR_STATE = -4,       /* call not valid in the sim's current state          */
+  TWS_ERR_UNSUPPORTED = -5  /* feature compiled out (e.g. GL interop)             */
+} tws_status;
+
+/* Which kernels run a step.  All three produce bit-identical state. */
+typedef enum tws_backend {
+  TWS_BACKEND_UNFUSED = 1,  /* two kernels per step, mirroring the two dispatches of
+                               Terrain.cpp:255-264 (in-place, no shared memory)          */
+  TWS_BACKEND_FUSED = 2,    /* one TMA-staged shared-memory stencil kernel per step      */
+  TWS_BACKEND_FUSED_TB = 3  /* fused + temporal blocking: `temporal_block` steps per HBM
+                               round trip                                                */
+} tws_backend;
+
+typedef enum tws_boundary {
+  TWS_BOUNDARY_REFERENCE_OPEN = 0, /* the reference: texels outside the grid read as 0
+                                      (flowUpdate.comp:18 / flowApply.comp:20 with
+                                      out-of-range imageLoad), water drains off the map */
+  TWS_BOUNDARY_CLOSED = 1          /* EXTENSION: no flow across the grid edge            */
+} tws_boundary;
+
+/* Fields for upload / readback.  Element counts are per cell of the sim's own rows. */
+typedef enum tws_field {
+  TWS_FIELD_TERRAIN = 0,      /* float  x1  terrain height   = TerrainData.r (Terrain.cpp:216) */
+  TWS_FIELD_WATER = 1,        /* float  x1  water depth      = TerrainData.a (Terrain.cpp:219) */
+  TWS_FIELD_FLUX = 2,         /* float  x4  outflow (+X,-X,+Y,-Y) = m_waterOutgoingFlow RGBA32F
+                                            (Terrain.cpp:230-234, flowUpdate.comp:44-47)        */
+  TWS_FIELD_VELOCITY = 3,     /* half   x2  flow vector      = m_waterFlowMap RG16F
+                                            (Terrain.cpp:236-237, flowApply.comp:45-52);
+                                            readback only, undefined before the first step     */
+  TWS_FIELD_TERRAIN_INFO = 4  /* float  x4  (r=terrain, g=b=0.3, a=water) = m_terrainData
+                                            RGBA32F exactly as the renderer samples it;
+                                            upload ignores g,b                                  */
+} tws_field;
+
+/* Creation parameters.  Set `size = sizeof(tws_params)`; use tws_default_params first. */
+typedef struct tws_params {
+  uint32_t size;
+  int32_t  width;             /* global grid width  (m_gridResolution, Terrain.cpp:23)       */
+  int32_t  height;            /* global grid height (the reference is square)                */
+  int32_t  row_begin;         /* first global row owned by this sim (0 for a whole grid)     */
+  int32_t  row_end;           /* one past the last owned row (height for a whole grid)       */
+  float    world_size;        /* m_gridWorldSize, Terrain.cpp:22 — cellDistance = world_size/width */
+  float    steps_per_second;  /* Terrain::SetSimulationStepsPerSecond, default 60            */
+  float    flow_damping;      /* Terrain::SetFlowDamping,        default 0.98                */
+  float    flow_acceleration; /* Terrain::SetFlowAcceleration,   default 10                  */
+  int32_t  boundary;          /* tws_boundary                                                */
+  int32_t  backend;           /* tws_backend                                                 */
+  int32_t  temporal_block;    /* steps fused per launch for FUSED_TB (1..4); ignored otherwise */
+  int32_t  device;            /* CUDA device ordinal                                         */
+  float    rain_rate;         /* EXTENSION: uniform depth added per second (0 = off)         */
+  float    evaporation_rate;  /* EXTENSION: uniform depth removed per second (0 = off)       */
+} tws_params;
+
+/* The three per-step scalars of the `SimulationParameters` UBO (simulationCommon.glsl:1-13). */
+typedef struct tws_step_constants {
+  float flow_friction_per_step;      /* powf(damping, (float)dt)                  Terrain.cpp:190 */
+  float water_acceleration_per_step; /* (float)(dt * acceleration * cellDistance) Terrain.cpp:197 */
+  float cell_area_inv_time_scaled;   /* (float)(dt / cellDistance^2)              Terrain.cpp:184 */
+} tws_step_constants;
+
+/* Peer wiring of one strip for multi-GPU runs (see tws_halo_* below). */
+#define TWS_IPC_HANDLE_BYTES 64
+typedef struct tws_halo_handle {
+  uint8_t  mem[TWS_IPC_HANDLE_BYTES];   /* cudaIpcMemHandle_t of the strip's state slab   */
+  uint64_t slab_bytes;
+  int32_t  row_begin, row_end;          /* for validation by the importer                  */
+  int32_t  device;
+  int32_t  pid;
+  uint64_t local_ptr;                   /* slab address, valid inside process `pid` only  */
+} tws_halo_handle;
+
+const char* tws_version(void);
+int32_t     tws_abi_version(void);
+
+/* Reference defaults: 1024x1024, world 1024, 60 steps/s, damping 0.98, acceleration 10
+ * (Terrain.cpp:21-30), open boundary, FUSED backend, whole grid on device 0. */
+void tws_default_params(tws_params* p);
+
+/* Replaces Terrain::Terrain + texture creation (Terrain.cpp:21-121,200-238): allocates
+ * the state on the device, zero-initialised (flux = 0 as Terrain.cpp:230-234). */
+tws_status tws_create(const tws_params* p, tws_sim** out);
+tws_status tws_destroy(tws_sim* s);
+const char* tws_last_error(const tws_sim* s);   /* s may be NULL: last tws_create failure */
+
+/* Replaces Set{SimulationStepsPerSecond,FlowDamping,FlowAcceleration} (Terrain.cpp:175-198).
+ * A negative/NaN argument is TWS_ERR_INVALID.  Takes effect at the next step, like the
+ * UBO upload at the next BindBuffer (UniformBuffer.cpp:122-153). */
+tws_status tws_set_steps_per_second(tws_sim* s, float steps_per_second);
+tws_status tws_set_flow_damping(tws_sim* s, float damping);
+tws_status tws_set_flow_acceleration(tws_sim* s, float acceleration);
+tws_status tws_set_sources(tws_sim* s, float rain_rate, float evaporation_rate);   /* EXTENSION */
+tws_status tws_get_step_constants(const tws_sim* s, tws_step_constants* out);
+
+/* Replaces Texture2D::SetData uploads (Terrain.cpp:223,233).  `host` holds the sim's own
+ * rows, tightly packed.  Uploading TERRAIN/WATER/FLUX does not touch the other fields. */
+tws_status tws_upload(tws_sim* s, tws_field field, const void* host, size_t bytes);
+tws_status tws_readback(tws_sim* s, tws_field field, void* host, size_t bytes);
+
+/* Replaces Terrain::CreateHeightmapFromNoiseAndResetSim (Terrain.cpp:200-238) with
+ * Random::Init(seed) (Application.cpp:57) in front: value-noise terrain (octaves
+ * lo..hi, persistence; reference 2,10,0.43), central lake, flux = 0 — generated on the
+ * GPU, bit-identical to the reference's CPU fill. */
+tws_status tws_reset_reference_scene(tws_sim* s, uint32_t seed, float height_scale,
+                                     int32_t octave_lo, int32_t octave_hi, float persistence);
+
+/* Replaces Terrain::ApplyRadialWaterBrush (Terrain.cpp:150-168) + waterBrush.comp:
+ * tws_inject_brush_world takes the world XZ position like the reference and derives the
+ * texel centre (Terrain.cpp:152-155); tws_inject_brush takes the texel-space centre
+ * (global coordinates).  Only the brush's bounding box is touched, result identical to
+ * the reference's whole-grid pass.  size_sq is 32 in the reference (Terrain.cpp:159). */
+tws_status tws_inject_brush(tws_sim* s, float center_x, float center_y, float intensity, float size_sq);
+tws_status tws_inject_brush_world(tws_sim* s, float world_x, float world_z, float strength);
+
+/* n x (flowUpdate; flowApply) — the loop body of Terrain.cpp:253-265, no clamp on n. */
+tws_status tws_step(tws_sim* s, int32_t n);
+
+/* Replaces Terrain::PerformSimulationStep(ezTime) (Terrain.cpp:240-277): frame-time
+ * accumulator, n = (uint)(acc/dt), acc -= dt*n, n = min(n,10); runs n steps and returns
+ * n through steps_done (may be NULL). */
+tws_status tws_advance(tws_sim* s, double frame_seconds, uint32_t* steps_done);
+
+/* fp64 sum of the water depth over the sim's own rows (volume check). Synchronises. */
+tws_status tws_total_volume(tws_sim* s, double* volume);
+tws_status tws_sync(tws_sim* s);
+
+/* Device-side timing of the most recent tws_step/tws_advance batch (CUDA events on the
+ * launching stream; replaces gl::TimerQuery around PerformSimulationStep,
+ * Scene.cpp:362-364).  Synchronises on the end event. */
+tws_status tws_elapsed_ms(tws_sim* s, float* ms);
+/* Number of kernels launched by this sim since creation. */
+uint64_t   tws_kernel_launches(const tws_sim* s);
+/* Raw device pointer and row pitch (in elements) of a planar field for zero-copy
+ * consumers (CUDA interop); planes: TERRAIN, WATER (current), VELOCITY. */
+tws_status tws_device_view(tws_sim* s, tws_field field, void** device_ptr, int64_t* pitch_elems);
+
+/* ---- multi-GPU strips: halo exchange over NVLink peer memory ----------------------
+ * One sim per GPU owns rows [row_begin,row_end).  After creation each sim exports a
+ * handle; the owner passes the handles of the strip above (rows < row_begin) and below
+ * (rows >= row_end) to tws_halo_connect (NULL = global edge).  Sims in one process use
+ * cudaDeviceEnablePeerAccess, sims in different processes CUDA IPC.  During tws_step
+ * each strip pushes its freshly computed edge rows into the neighbours' halo rows and
+ * raises a step flag in the neighbour's memory; the neighbour's edge kernels wait on
+ * that flag while its interior kernels run.  tws_halo_refresh pushes the current state
+ * (after upload / reset / inject); call it on all strips, then tws_sync + a host barrier. */
+tws_status tws_halo_export(tws_sim* s, tws_halo_handle* out);
+tws_status tws_halo_connect(tws_sim* s, const tws_halo_handle* up, const tws_halo_handle* down);
+tws_status tws_halo_refresh(tws_sim* s);
+
+/* ---- renderer hand-off (CUDA-GL interop) --------------------------------------------
+ * Registers the renderer's two textures: TerrainInfo RGBA32F (m_terrainData) and
+ * FlowMap RG16F (m_waterFlowMap); tws_gl_publish writes (r=terrain,g=b=0.3,a=water)
+ * and the flow vector into them.  Built only with -DTWS_WITH_GL (needs GL headers);
+ * otherwise TWS_ERR_UNSUPPORTED.  tws_publish_packed is the same pack step into plain
+ * device buffers the library owns (testable without GL). */
+tws_status tws_gl_register(tws_sim* s, uint32_t terrain_info_tex, uint32_t flow_map_tex);
+tws_status tws_gl_publish(tws_sim* s);
+tws_status tws_gl_unregister(tws_sim* s);
+tws_status tws_publish_packed(tws_sim* s, void** terrain_info_rgba32f_dev, void** flow_map_rg16f_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TWS_H_ */

@@ -1,0 +1,220 @@
+// aux_kernels.cu — everything around the step: inject (waterBrush.comp), create/reset
+// (Terrain.cpp:200-238 on the GPU), layout packing for the reference's RGBA textures,
+// the fp64 volume reduction, and the NVLink halo push / step flags of the strip exchange.
+// Built with -fmad=false like step_kernels.cu (same arithmetic contract).
+#include "tws_internal.h"
+
+#include <cuda_fp16.h>
+
+namespace tws {
+
+// ---- inject: waterBrush.comp:20-31 over the brush's bounding box only -------------------
+// Cells outside the box get saturate(1 - dist) == 0 exactly, so d + 0*intensity == d and
+// the result equals the reference's whole-grid pass bit for bit.
+__global__ void brush_kernel(Geom g, float* d /* local row 0 */, float cx, float cy, float intensity, float size_sq,
+                             int bx0, int by0, int bw, int bh) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ix >= bw || iy >= bh) return;
+  const int x = bx0 + ix, gy = by0 + iy;               // global texel
+  const float tx = cx - (float)x, ty = cy - (float)gy;                               // :26
+  const float dist = __fdiv_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)), size_sq);   // :27
+  float s = 1.0f - dist;                                                             // :28
+  s = (s < 0.0f) ? 0.0f : ((s > 1.0f) ? 1.0f : s);
+  const long long o = (long long)(gy - g.row0) * g.pitch + x;
+  d[o] = __fadd_rn(d[o], __fmul_rn(s, intensity));
+}
+
+cudaError_t launch_brush(const Geom& g, float* d, float cx, float cy, float intensity, float size_sq, cudaStream_t st, int* launched) {
+  *launched = 0;
+  if (!(size_sq > 0.0f) || !isfinite(cx) || !isfinite(cy)) return cudaSuccess;       // NaN/0 size: reference adds 0*i or NaN; we refuse upstream
+  const float rad = ceilf(sqrtf(size_sq)) + 1.0f;
+  // Box in global texels, clipped to the rows this strip stores (own rows + live halos).
+  const double lo_x = floor((double)cx - rad), hi_x = ceil((double)cx + rad);
+  const double lo_y = floor((double)cy - rad), hi_y = ceil((double)cy + rad);
+  const int row_lo = g.row0 - (g.has_up ? TWS_HALO_ROWS : 0), row_hi = g.row0 + g.rows + (g.has_down ? TWS_HALO_ROWS : 0);
+  const int x0 = (int)fmax(lo_x, 0.0), x1 = (int)fmin(hi_x, (double)g.W - 1);
+  const int y0 = (int)fmax(lo_y, (double)row_lo), y1 = (int)fmin(hi_y, (double)row_hi - 1);
+  if (x1 < x0 || y1 < y0) return cudaSuccess;
+  const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+  dim3 block(16, 16), grid((bw + 15) / 16, (bh + 15) / 16);
+  brush_kernel<<<grid, block, 0, st>>>(g, d, cx, cy, intensity, size_sq, x0, y0, bw, bh);
+  *launched = 1;
+  return cudaGetLastError();
+}
+
+// ---- create/reset: NoiseGenerator.cpp:12-97 + Terrain.cpp:209-219 ------------------------
+__device__ __forceinline__ int noise_floor(float a) { int r = (int)a; return r - (int)((a < 0) && (a - (float)r != 0.0f)); }
+__device__ __forceinline__ float noise_smooth(float f) { return f * f * f * (f * (f * 6.0f - 15.0f) + 10.0f); }
+
+__device__ float noise3d(const float* white, float cx, float cy, float cz, int period) {
+  period = period < 16 ? period : 16;                  // min<uint>(period, 16); period >= 1 here
+  const int mod = period - 1;
+  int x0 = noise_floor(cx), y0 = noise_floor(cy), z0 = noise_floor(cz);
+  const float fx = cx - (float)x0, fy = cy - (float)y0, fz = cz - (float)z0;
+  x0 = (x0 % period + period) & mod; y0 = (y0 % period + period) & mod; z0 = (z0 % period + period) & mod;
+  const int x1 = (x0 + 1) & mod, y1 = (y0 + 1) & mod, z1 = (z0 + 1) & mod;
+  const float s000 = white[x0 + 16 * (y0 + 16 * z0)], s100 = white[x1 + 16 * (y0 + 16 * z0)];
+  const float s010 = white[x0 + 16 * (y1 + 16 * z0)], s110 = white[x1 + 16 * (y1 + 16 * z0)];
+  const float s001 = white[x0 + 16 * (y0 + 16 * z1)], s101 = white[x1 + 16 * (y0 + 16 * z1)];
+  const float s011 = white[x0 + 16 * (y1 + 16 * z1)], s111 = white[x1 + 16 * (y1 + 16 * z1)];
+  const float u = noise_smooth(fx), v = noise_smooth(fy), w = noise_smooth(fz);
+  const float uv = u * v, uw = u * w, vw = v * w;
+  const float k0 = s000, k1 = s100 - s000, k2 = s010 - s000, k3 = s001 - s000;
+  const float k4 = s110 - s010 - k1;
+  const float k5 = s000 - s010 - s001 + s011;
+  const float k6 = -k1 - s001 + s101;
+  const float k7 = -k4 + s001 - s101 - s011 + s111;
+  return k0 + k1 * u + k2 * v + k3 * w + k4 * uv + k5 * vw + k6 * uw + k7 * uv * w;
+}
+
+__global__ void __launch_bounds__(256) scene_kernel(Geom g, float* h, float* d /* local row 0 */, const float* __restrict__ white_g,
+                                                    float height_scale, int lo, int hi, float persistence, int lr0, int lr1) {
+  __shared__ float white[4096];
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) white[i] = white_g[i];
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= g.W) return;
+  const float mx = __fdiv_rn(1.0f, (float)(g.W - 1)), my = __fdiv_rn(1.0f, (float)(g.Hg - 1));
+  for (int lr = lr0 + blockIdx.y; lr < lr1; lr += gridDim.y) {
+    const int gy = g.row0 + lr;
+    const float cx = mx * (float)x, cy = my * (float)gy, cz = 0.0f;
+    float res = 0.0f, amplitude = 1.0f, frequency = (float)(1 << lo);
+    for (int i = lo; i <= hi; ++i) {
+      res += amplitude * (noise3d(white, cx * frequency, cy * frequency, cz * frequency, (int)frequency) * 0.5f + 0.5f);
+      amplitude *= persistence;
+      frequency *= 2.0f;
+    }
+    const float n = __fdiv_rn(res * 2.0f * (1.0f - persistence), (1.0f - amplitude)) - 1.0f;
+    const float terrain = (n * 0.5f + 0.5f) * height_scale;
+    const float px = (float)x * mx - 0.5f, py = (float)gy * my - 0.5f;
+    const float l2 = px * px + py * py;
+    const float p = l2 * l2;                             // pow(l2, 2.0f): exact product, correctly rounded
+    const float water = (0.45f - p * 800.0f) * height_scale - terrain;
+    const long long o = (long long)lr * g.pitch + x;
+    h[o] = terrain;
+    d[o] = (0.0f < water) ? water : 0.0f;                // std::max(0.0f, water)
+  }
+}
+
+cudaError_t launch_scene(const Geom& g, const Planes& p, int side, const float* white_dev, float height_scale, int lo, int hi,
+                         float persistence, cudaStream_t st) {
+  const size_t off = (size_t)TWS_HALO_ROWS * g.pitch;
+  const int lr0 = g.has_up ? -TWS_HALO_ROWS : 0, lr1 = g.rows + (g.has_down ? TWS_HALO_ROWS : 0);
+  dim3 block(256), grid((g.W + 255) / 256, (lr1 - lr0) < 4096 ? (lr1 - lr0) : 4096);
+  scene_kernel<<<grid, block, 0, st>>>(g, p.h + off, p.d[side] + off, white_dev, height_scale, lo, hi, persistence, lr0, lr1);
+  return cudaGetLastError();
+}
+
+// ---- layout packing -------------------------------------------------------------------------
+// Flux: planar (+X,-X,+Y,-Y) <-> the reference's RGBA32F texel (m_waterOutgoingFlow).
+__global__ void pack_flux_kernel(Geom g, float* f0, float* f1, float* f2, float* f3, float4* aos, int lr0, int nrows, int to_aos) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= g.W) return;
+  for (int r = blockIdx.y; r < nrows; r += gridDim.y) {
+    const long long o = (long long)(lr0 + r) * g.pitch + x;
+    const long long a = (long long)r * g.W + x;
+    if (to_aos) aos[a] = make_float4(f0[o], f1[o], f2[o], f3[o]);
+    else { const float4 v = aos[a]; f0[o] = v.x; f1[o] = v.y; f2[o] = v.z; f3[o] = v.w; }
+  }
+}
+// TerrainInfo: (r = terrain, g = b = 0.3, a = water) <-> planar h, d  (Terrain.cpp:216-219).
+__global__ void pack_info_kernel(Geom g, float* h, float* d, float4* aos, int lr0, int nrows, int to_aos) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= g.W) return;
+  for (int r = blockIdx.y; r < nrows; r += gridDim.y) {
+    const long long o = (long long)(lr0 + r) * g.pitch + x;
+    const long long a = (long long)r * g.W + x;
+    if (to_aos) aos[a] = make_float4(h[o], 0.3f, 0.3f, d[o]);
+    else { const float4 v = aos[a]; h[o] = v.x; d[o] = v.w; }
+  }
+}
+
+cudaError_t launch_pack_flux(const Geom& g, const Planes& p, int side, float* aos, int lr0, int nrows, bool to_aos, cudaStream_t st) {
+  const size_t off = (size_t)TWS_HALO_ROWS * g.pitch;
+  dim3 block(256), grid((g.W + 255) / 256, nrows < 1024 ? nrows : 1024);
+  pack_flux_kernel<<<grid, block, 0, st>>>(g, p.F[side][0] + off, p.F[side][1] + off, p.F[side][2] + off, p.F[side][3] + off,
+                                           (float4*)aos, lr0, nrows, to_aos ? 1 : 0);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_info(const Geom& g, const Planes& p, int side, float* aos, int lr0, int nrows, bool to_aos, cudaStream_t st) {
+  const size_t off = (size_t)TWS_HALO_ROWS * g.pitch;
+  dim3 block(256), grid((g.W + 255) / 256, nrows < 1024 ? nrows : 1024);
+  pack_info_kernel<<<grid, block, 0, st>>>(g, p.h + off, p.d[side] + off, (float4*)aos, lr0, nrows, to_aos ? 1 : 0);
+  return cudaGetLastError();
+}
+
+// ---- fp64 volume: fixed-shape two-stage reduction (deterministic) ------------------------------
+__global__ void __launch_bounds__(256) volume_kernel(Geom g, const float* __restrict__ d /* local row 0 */, double* partials) {
+  double acc = 0.0;
+  for (int r = blockIdx.x; r < g.rows; r += gridDim.x) {
+    const float* row = d + (long long)r * g.pitch;
+    for (int x = threadIdx.x; x < g.W; x += blockDim.x) acc += (double)row[x];
+  }
+  __shared__ double sm[256];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = sm[0];
+}
+cudaError_t launch_volume(const Geom& g, const float* d, double* partials, int nblocks, cudaStream_t st) {
+  volume_kernel<<<nblocks, 256, 0, st>>>(g, d + (size_t)TWS_HALO_ROWS * g.pitch, partials);
+  return cudaGetLastError();
+}
+
+// ---- strip exchange: push edge rows into the neighbours' halo rows over NVLink ----------------
+__global__ void __launch_bounds__(256) row_copy_kernel(RowCopy a, RowCopy b, int ncopies) {
+  const RowCopy& c = (blockIdx.z == 0) ? a : b;
+  if ((int)blockIdx.z >= ncopies) return;
+  const int n4 = c.pitch / 4;
+  for (int pl = blockIdx.y; pl < c.nplanes; pl += gridDim.y) {
+    const float4* src = reinterpret_cast<const float4*>(c.src[pl] + (long long)c.src_row * c.pitch);
+    float4* dst = reinterpret_cast<float4*>(c.dst[pl] + (long long)c.dst_row * c.pitch);
+    const long long total = (long long)n4 * c.nrows;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+  }
+  __threadfence_system();
+}
+cudaError_t launch_row_copy(const RowCopy& a, const RowCopy& b, int ncopies, cudaStream_t st) {
+  if (ncopies <= 0) return cudaSuccess;
+  const int np = a.nplanes > b.nplanes ? a.nplanes : b.nplanes;
+  dim3 grid(32, np, ncopies);
+  row_copy_kernel<<<grid, 256, 0, st>>>(a, b, ncopies);
+  return cudaGetLastError();
+}
+
+__global__ void post_flags_kernel(volatile uint32_t* up_flag, volatile uint32_t* down_flag, uint32_t value) {
+  __threadfence_system();
+  if (up_flag) *up_flag = value;
+  if (down_flag) *down_flag = value;
+  __threadfence_system();
+}
+cudaError_t launch_post_flags(volatile uint32_t* up_flag, volatile uint32_t* down_flag, uint32_t value, cudaStream_t st) {
+  post_flags_kernel<<<1, 1, 0, st>>>(up_flag, down_flag, value);
+  return cudaGetLastError();
+}
+
+// Spin until both neighbours have published epoch >= value.  Bounded: after ~20 s the
+// kernel gives up and raises ctrl->error so a dead peer cannot hang the GPU.
+__global__ void wait_flags_kernel(Control* ctrl, int wait_up, int wait_down, uint32_t value) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    const bool ok_up = !wait_up || (int32_t)(ctrl->flag_from_up - value) >= 0;
+    const bool ok_dn = !wait_down || (int32_t)(ctrl->flag_from_down - value) >= 0;
+    if (ok_up && ok_dn) break;
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 20000000000ull) { ctrl->error = 1u; break; }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+cudaError_t launch_wait_flags(Control* ctrl, int wait_up, int wait_down, uint32_t value, cudaStream_t st) {
+  wait_flags_kernel<<<1, 1, 0, st>>>(ctrl, wait_up, wait_down, value);
+  return cudaGetLastError();
+}
+
+}  // namespace tws

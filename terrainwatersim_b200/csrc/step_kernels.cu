@@ -1,0 +1,452 @@
+// step_kernels.cu — the shallow-water step on sm_100a.
+//
+// Replaces flowUpdate.comp:12-63 + flowApply.comp:14-53 (dispatched at Terrain.cpp:255-264).
+// Arithmetic contract: IEEE fp32, the shader's operation
+// order, NO fma contraction (file is built with -fmad=false and the two a*b+c*d sites use
+// __fmul_rn/__fadd_rn explicitly), IEEE division, max(0,x) == (x > 0 ? x : 0), exterior
+// texels read as 0, velocity stored as 2 x fp16 round-to-nearest-even.  Every kernel in
+// this file produces bit-identical state; tests compare them with the CPU oracle.
+//
+// Kernels:
+//   unfused_update_kernel / unfused_apply_kernel — the two reference dispatches, planar,
+//       in place, neighbours through L1/L2 (baseline, BASELINE.json config 2).
+//   fused_step_kernel<K,OX,OY,NT> — K whole steps per HBM round trip.  One CTA stages an
+//       (OX+2HX) x (OY+4K) tile of h, d and the four flux planes in shared memory with six
+//       TMA tensor loads (out-of-bounds zero fill IS the reference's exterior rule), runs
+//       2K in-place passes over a region shrinking by one cell per pass, and writes the
+//       OX x OY centre straight from registers (flux after the last flux pass, depth and
+//       velocity after the last depth pass).  HBM traffic per cell: 24 B read + 24 B
+//       written per K cell-updates (+ halo over-fetch, mostly served by L2).
+#include "tws_internal.h"
+
+#include <cuda_fp16.h>
+
+namespace tws {
+
+// ------------------------------------------------------------------------------------
+// cell arithmetic shared by all kernels
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float max0(float v) { return (v > 0.0f) ? v : 0.0f; }   // flowUpdate.comp:54
+
+// flowUpdate.comp:44-59.  f* in: old outflow, out: new outflow.
+__device__ __forceinline__ void flux_cell(float Hc, float Hxp, float Hxm, float Hyp, float Hym, float depth,
+                                          float& fx, float& fy, float& fz, float& fw, const StepConsts& c) {
+  float nx = Hc - Hxp, ny = Hc - Hxm, nz = Hc - Hyp, nw = Hc - Hym;                  // :44-47
+  nx = __fadd_rn(__fmul_rn(fx, c.friction), __fmul_rn(nx, c.accel));                 // :53
+  ny = __fadd_rn(__fmul_rn(fy, c.friction), __fmul_rn(ny, c.accel));
+  nz = __fadd_rn(__fmul_rn(fz, c.friction), __fmul_rn(nz, c.accel));
+  nw = __fadd_rn(__fmul_rn(fw, c.friction), __fmul_rn(nw, c.accel));
+  nx = max0(nx); ny = max0(ny); nz = max0(nz); nw = max0(nw);                        // :54
+  const float total = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(nx, ny), nz), nw), c.area_inv);   // :57
+  if (total > depth) {                                                               // :58
+    const float s = __fdiv_rn(depth, total);                                         // :59
+    nx = __fmul_rn(nx, s); ny = __fmul_rn(ny, s); nz = __fmul_rn(nz, s); nw = __fmul_rn(nw, s);
+  }
+  fx = nx; fy = ny; fz = nz; fw = nw;
+}
+
+// flowApply.comp:38-46.  Returns the new depth; vx, vy the flow vector.
+__device__ __forceinline__ float apply_cell(float depth, float fx, float fy, float fz, float fw, float iX1, float iX0,
+                                            float iY1, float iY0, const StepConsts& c, float& vx, float& vy) {
+  const float in = __fadd_rn(__fadd_rn(__fadd_rn(iX1, iX0), iY1), iY0);              // :38
+  const float out = __fadd_rn(__fadd_rn(__fadd_rn(fx, fy), fz), fw);                 // :39
+  float nd = max0(__fadd_rn(depth, __fmul_rn(__fsub_rn(in, out), c.area_inv)));      // :41
+  if (c.ext_sources) nd = max0(__fsub_rn(__fadd_rn(nd, c.rain_step), c.evap_step));  // EXT
+  vx = __fsub_rn(__fsub_rn(iX1, fx), __fsub_rn(iX0, fy));                            // :45
+  vy = __fsub_rn(__fsub_rn(iY1, fz), __fsub_rn(iY0, fw));                            // :46
+  return nd;
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float x, float y) {                  // rg16f store, :52
+  const __half2 h = __floats2half2_rn(x, y);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+// ------------------------------------------------------------------------------------
+// unfused baseline: one thread per 4 consecutive cells, float4 global access
+// ------------------------------------------------------------------------------------
+// All plane pointers address LOCAL row 0 (plane row TWS_HALO_ROWS).  Rows lr0..lr1-1 are
+// processed; rows outside the GLOBAL grid read as 0.
+__global__ void __launch_bounds__(256) unfused_update_kernel(Geom g, const float* __restrict__ h, const float* __restrict__ d,
+                                                             float* Fxp, float* Fxm, float* Fyp, float* Fym,
+                                                             StepConsts c, int lr0, int lr1) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x >= g.pitch) return;
+  for (int lr = lr0 + blockIdx.y; lr < lr1; lr += gridDim.y) {
+  const int gy = g.row0 + lr;
+  const long long o = (long long)lr * g.pitch + x;
+  const bool up_ok = gy - 1 >= 0, dn_ok = gy + 1 < g.Hg;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 dC = ld4(d + o), hC = ld4(h + o);
+  const float4 HC = add4(dC, hC);                                                    // a + r, flowUpdate.comp:34
+  float4 HU = up_ok ? add4(ld4(d + o - g.pitch), ld4(h + o - g.pitch)) : z4;       // y-1
+  float4 HD = dn_ok ? add4(ld4(d + o + g.pitch), ld4(h + o + g.pitch)) : z4;       // y+1
+  float HL = (x > 0) ? (d[o - 1] + h[o - 1]) : 0.0f;
+  float HR = (x + 4 < g.pitch) ? (d[o + 4] + h[o + 4]) : 0.0f;
+  float4 fx = ld4(Fxp + o), fy = ld4(Fxm + o), fz = ld4(Fyp + o), fw = ld4(Fym + o);
+  float* pfx = &fx.x; float* pfy = &fy.x; float* pfz = &fz.x; float* pfw = &fw.x;
+  const float Hc[4] = {HC.x, HC.y, HC.z, HC.w};
+  const float Hu[4] = {HU.x, HU.y, HU.z, HU.w};
+  const float Hd[4] = {HD.x, HD.y, HD.z, HD.w};
+  const float dc[4] = {dC.x, dC.y, dC.z, dC.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gx = x + i;
+    float hxp = (i < 3) ? Hc[i + 1] : HR;
+    float hxm = (i > 0) ? Hc[i - 1] : HL;
+    float hyp = Hd[i], hym = Hu[i];
+    if (c.closed) {
+      if (gx + 1 >= g.W) hxp = Hc[i];
+      if (gx - 1 < 0) hxm = Hc[i];
+      if (!dn_ok) hyp = Hc[i];
+      if (!up_ok) hym = Hc[i];
+    }
+    flux_cell(Hc[i], hxp, hxm, hyp, hym, dc[i], pfx[i], pfy[i], pfz[i], pfw[i], c);
+    if (gx >= g.W) { pfx[i] = 0.f; pfy[i] = 0.f; pfz[i] = 0.f; pfw[i] = 0.f; }      // pad columns stay 0
+  }
+  st4(Fxp + o, fx); st4(Fxm + o, fy); st4(Fyp + o, fz); st4(Fym + o, fw);
+  }
+}
+
+__global__ void __launch_bounds__(256) unfused_apply_kernel(Geom g, float* d, const float* __restrict__ Fxp,
+                                                            const float* __restrict__ Fxm, const float* __restrict__ Fyp,
+                                                            const float* __restrict__ Fym, uint32_t* __restrict__ v,
+                                                            StepConsts c, int lr0, int lr1) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x >= g.pitch) return;
+  for (int lr = lr0 + blockIdx.y; lr < lr1; lr += gridDim.y) {
+  const int gy = g.row0 + lr;
+  const long long o = (long long)lr * g.pitch + x;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 fx = ld4(Fxp + o), fy = ld4(Fxm + o), fz = ld4(Fyp + o), fw = ld4(Fym + o);
+  const float4 iy1 = (gy + 1 < g.Hg) ? ld4(Fym + o + g.pitch) : z4;                  // F(x,y+1).w, flowApply.comp:34
+  const float4 iy0 = (gy - 1 >= 0) ? ld4(Fyp + o - g.pitch) : z4;                    // F(x,y-1).z, :35
+  const float l = (x > 0) ? Fxp[o - 1] : 0.0f;                                       // F(x-1,y).x, :33
+  const float r = (x + 4 < g.pitch) ? Fxm[o + 4] : 0.0f;                             // F(x+1,y).y, :32
+  const float4 dC = ld4(d + o);
+  float nd[4]; uint32_t nv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float iX1 = (i < 3) ? comp(fy, i + 1) : r;
+    const float iX0 = (i > 0) ? comp(fx, i - 1) : l;
+    float vx, vy;
+    nd[i] = apply_cell(comp(dC, i), comp(fx, i), comp(fy, i), comp(fz, i), comp(fw, i), iX1, iX0, comp(iy1, i), comp(iy0, i), c, vx, vy);
+    nv[i] = pack_half2(vx, vy);
+    if (x + i >= g.W) { nd[i] = 0.f; nv[i] = 0u; }
+  }
+  st4(d + o, make_float4(nd[0], nd[1], nd[2], nd[3]));
+  *reinterpret_cast<uint4*>(v + o) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// fused / temporally blocked kernel
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int K, int OX_, int OY_, int NT_>
+struct FusedCfg {
+  static constexpr int OX = OX_, OY = OY_, NT = NT_;
+  static constexpr int HX = ((2 * K + 3) / 4) * 4;   // x halo rounded to whole float4 groups
+  static constexpr int HY = 2 * K;
+  static constexpr int SX = OX + 2 * HX, SY = OY + 2 * HY;
+  static constexpr int PLANE = SX * SY;              // floats per staged plane
+  static constexpr size_t SMEM = (size_t)6 * PLANE * sizeof(float);
+  static_assert(OX % 4 == 0 && SX <= 256 && SY <= 256, "TMA box limits");
+  static_assert((PLANE * 4) % 128 == 0, "staged planes must keep 128 B alignment");
+};
+
+struct FusedOut {          // plane pointers at local row 0
+  float* d; float* F[4]; uint32_t* v;
+};
+
+template <class C, int K>
+__global__ void __launch_bounds__(C::NT) fused_step_kernel(const __grid_constant__ CUtensorMap tm_h,
+                                                           const __grid_constant__ CUtensorMap tm_d,
+                                                           const __grid_constant__ CUtensorMap tm_f0,
+                                                           const __grid_constant__ CUtensorMap tm_f1,
+                                                           const __grid_constant__ CUtensorMap tm_f2,
+                                                           const __grid_constant__ CUtensorMap tm_f3,
+                                                           FusedOut out, Geom g, StepConsts c, int ty0, int tma_y_bias) {
+  constexpr int OX = C::OX, OY = C::OY, NT = C::NT, HX = C::HX, HY = C::HY, SX = C::SX, PLANE = C::PLANE;
+  extern __shared__ __align__(1024) float smem[];
+  __shared__ uint64_t bar;
+  float* sh = smem;
+  float* sd = smem + PLANE;
+  float* sFxp = smem + 2 * PLANE;
+  float* sFxm = smem + 3 * PLANE;
+  float* sFyp = smem + 4 * PLANE;
+  float* sFym = smem + 5 * PLANE;
+
+  const int tid = threadIdx.x;
+  const int ox0 = blockIdx.x * OX;                   // first output column
+  const int oy0 = (ty0 + blockIdx.y) * OY;           // first output LOCAL row
+  const int sx0 = ox0 - HX, sy0 = oy0 - HY;          // staged origin (grid x, local row)
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, (uint32_t)C::SMEM);
+    const int ty = sy0 + tma_y_bias;
+    tma_load_2d(sh, &tm_h, sx0, ty, &bar);
+    tma_load_2d(sd, &tm_d, sx0, ty, &bar);
+    tma_load_2d(sFxp, &tm_f0, sx0, ty, &bar);
+    tma_load_2d(sFxm, &tm_f1, sx0, ty, &bar);
+    tma_load_2d(sFyp, &tm_f2, sx0, ty, &bar);
+    tma_load_2d(sFym, &tm_f3, sx0, ty, &bar);
+  }
+  mbar_wait(&bar, 0);
+
+  const int gy_base = g.row0 + sy0;                  // global row of staged row 0
+
+#pragma unroll
+  for (int t = 1; t <= K; ++t) {
+    // ---------------- flux pass of level t: margin 2(K-t)+1 around the output tile ----
+    {
+      const int M = 2 * (K - t) + 1;
+      const int X0 = (HX - M) / 4, X1 = (HX + OX + M + 3) / 4, NG = X1 - X0;
+      const int R0 = HY - M, NR = OY + 2 * M;
+      const bool last = (t == K);
+      for (int it = tid; it < NG * NR; it += NT) {
+        const int rr = it / NG, gg = it - rr * NG;
+        const int r = R0 + rr, x = (X0 + gg) * 4;
+        const int o = r * SX + x;
+        const int gy = gy_base + r, gx0 = sx0 + x;
+        const float4 dC = ld4(sd + o);
+        const float4 HC = add4(dC, ld4(sh + o));
+        const float4 HU = add4(ld4(sd + o - SX), ld4(sh + o - SX));
+        const float4 HD = add4(ld4(sd + o + SX), ld4(sh + o + SX));
+        const float HL = sd[o - 1] + sh[o - 1];
+        const float HR = sd[o + 4] + sh[o + 4];
+        float4 fx = ld4(sFxp + o), fy = ld4(sFxm + o), fz = ld4(sFyp + o), fw = ld4(sFym + o);
+        float* pfx = &fx.x; float* pfy = &fy.x; float* pfz = &fz.x; float* pfw = &fw.x;
+        const bool row_in = (unsigned)gy < (unsigned)g.Hg;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int gx = gx0 + i;
+          const float Hc = comp(HC, i);
+          float hxp = (i < 3) ? comp(HC, i + 1) : HR;
+          float hxm = (i > 0) ? comp(HC, i - 1) : HL;
+          float hyp = comp(HD, i), hym = comp(HU, i);
+          if (c.closed) {
+            if (gx + 1 >= g.W) hxp = Hc;
+            if (gx - 1 < 0) hxm = Hc;
+            if (gy + 1 >= g.Hg) hyp = Hc;
+            if (gy - 1 < 0) hym = Hc;
+          }
+          flux_cell(Hc, hxp, hxm, hyp, hym, comp(dC, i), pfx[i], pfy[i], pfz[i], pfw[i], c);
+          if (!(row_in && (unsigned)gx < (unsigned)g.W)) { pfx[i] = 0.f; pfy[i] = 0.f; pfz[i] = 0.f; pfw[i] = 0.f; }
+        }
+        st4(sFxp + o, fx); st4(sFxm + o, fy); st4(sFyp + o, fz); st4(sFym + o, fw);
+        if (last) {
+          const int lr = sy0 + r;                      // local row
+          if (x >= HX && x < HX + OX && r >= HY && r < HY + OY && lr < g.rows && gx0 < g.pitch) {
+            const size_t go = (size_t)((long long)lr * g.pitch) + gx0;
+            st4(out.F[0] + go, fx); st4(out.F[1] + go, fy); st4(out.F[2] + go, fz); st4(out.F[3] + go, fw);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------- depth pass of level t: margin 2(K-t) ------------------------------
+    {
+      const int M = 2 * (K - t);
+      const int X0 = (HX - M) / 4, X1 = (HX + OX + M + 3) / 4, NG = X1 - X0;
+      const int R0 = HY - M, NR = OY + 2 * M;
+      const bool last = (t == K);
+      for (int it = tid; it < NG * NR; it += NT) {
+        const int rr = it / NG, gg = it - rr * NG;
+        const int r = R0 + rr, x = (X0 + gg) * 4;
+        const int o = r * SX + x;
+        const int gy = gy_base + r, gx0 = sx0 + x;
+        const float4 fx = ld4(sFxp + o), fy = ld4(sFxm + o), fz = ld4(sFyp + o), fw = ld4(sFym + o);
+        const float4 iy1 = ld4(sFym + o + SX);         // F(x,y+1).w
+        const float4 iy0 = ld4(sFyp + o - SX);         // F(x,y-1).z
+        const float l = sFxp[o - 1];                   // F(x-1,y).x
+        const float rgt = sFxm[o + 4];                 // F(x+1,y).y
+        const float4 dC = ld4(sd + o);
+        const bool row_in = (unsigned)gy < (unsigned)g.Hg;
+        float nd[4]; uint32_t nv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float iX1 = (i < 3) ? comp(fy, i + 1) : rgt;
+          const float iX0 = (i > 0) ? comp(fx, i - 1) : l;
+          float vx, vy;
+          nd[i] = apply_cell(comp(dC, i), comp(fx, i), comp(fy, i), comp(fz, i), comp(fw, i), iX1, iX0, comp(iy1, i),
+                             comp(iy0, i), c, vx, vy);
+          nv[i] = pack_half2(vx, vy);
+          if (!(row_in && (unsigned)(gx0 + i) < (unsigned)g.W)) { nd[i] = 0.f; nv[i] = 0u; }
+        }
+        if (!last) {
+          st4(sd + o, make_float4(nd[0], nd[1], nd[2], nd[3]));
+        } else {
+          const int lr = sy0 + r;
+          if (lr < g.rows && gx0 < g.pitch) {
+            const size_t go = (size_t)((long long)lr * g.pitch) + gx0;
+            st4(out.d + go, make_float4(nd[0], nd[1], nd[2], nd[3]));
+            *reinterpret_cast<uint4*>(out.v + go) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+          }
+        }
+      }
+    }
+    if (t < K) __syncthreads();
+  }
+}
+
+// ---- per-K tile configuration ---------------------------------------------------------
+template <int K> struct CfgFor;
+template <> struct CfgFor<1> { using type = FusedCfg<1, 128, 28, 256>; };
+template <> struct CfgFor<2> { using type = FusedCfg<2, 128, 24, 256>; };
+template <> struct CfgFor<3> { using type = FusedCfg<3, 112, 52, 512>; };
+template <> struct CfgFor<4> { using type = FusedCfg<4, 112, 48, 512>; };
+
+template <int K>
+static cudaError_t launch_fused_k(const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int ty0,
+                                  int ty1, cudaStream_t st) {
+  using C = typename CfgFor<K>::type;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = fused_step_kernel<C, K>;
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  const int dst = 1 - src;
+  const size_t row0_off = (size_t)TWS_HALO_ROWS * g.pitch;
+  FusedOut out;
+  out.d = p.d[dst] + row0_off;
+  for (int i = 0; i < 4; ++i) out.F[i] = p.F[dst][i] + row0_off;
+  out.v = p.v + row0_off;
+  dim3 grid((g.W + C::OX - 1) / C::OX, ty1 - ty0, 1);
+  if (grid.y == 0) return cudaSuccess;
+  const int bias = g.has_up ? TWS_HALO_ROWS : 0;
+  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], tma.m[2], tma.m[3], tma.m[4], tma.m[5], out, g, c, ty0, bias);
+  return cudaGetLastError();
+}
+
+int fused_out_rows_per_tile(int K) {
+  switch (K) {
+    case 1: return CfgFor<1>::type::OY;
+    case 2: return CfgFor<2>::type::OY;
+    case 3: return CfgFor<3>::type::OY;
+    default: return CfgFor<4>::type::OY;
+  }
+}
+int fused_tile_rows(int K, int rows) { const int oy = fused_out_rows_per_tile(K); return (rows + oy - 1) / oy; }
+
+cudaError_t launch_fused(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int ty0,
+                         int ty1, cudaStream_t st) {
+  switch (K) {
+    case 1: return launch_fused_k<1>(g, p, tma, src, c, ty0, ty1, st);
+    case 2: return launch_fused_k<2>(g, p, tma, src, c, ty0, ty1, st);
+    case 3: return launch_fused_k<3>(g, p, tma, src, c, ty0, ty1, st);
+    case 4: return launch_fused_k<4>(g, p, tma, src, c, ty0, ty1, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ---- TMA descriptors --------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+static void box_for(int K, int* sx, int* sy) {
+  switch (K) {
+    case 1: *sx = CfgFor<1>::type::SX; *sy = CfgFor<1>::type::SY; break;
+    case 2: *sx = CfgFor<2>::type::SX; *sy = CfgFor<2>::type::SY; break;
+    case 3: *sx = CfgFor<3>::type::SX; *sy = CfgFor<3>::type::SY; break;
+    default: *sx = CfgFor<4>::type::SX; *sy = CfgFor<4>::type::SY; break;
+  }
+}
+
+// Descriptors for reading side `side` with the K-level kernel.  The tensor covers the
+// rows that hold real data: own rows plus the halo rows towards an existing neighbour;
+// everything outside is the global exterior and is zero-filled by the TMA unit.
+cudaError_t fused_build_tma(int K, const Geom& g, const Planes& p, int side, TmaSet* out, std::string* err) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { if (err) *err = "cuTensorMapEncodeTiled not available from the driver"; return cudaErrorNotSupported; }
+  int sx, sy;
+  box_for(K, &sx, &sy);
+  const int first_row = g.has_up ? 0 : TWS_HALO_ROWS;   // plane row of the first visible row
+  const int vis_rows = g.rows + (g.has_up ? TWS_HALO_ROWS : 0) + (g.has_down ? TWS_HALO_ROWS : 0);
+  float* bases[6] = {p.h, p.d[side], p.F[side][0], p.F[side][1], p.F[side][2], p.F[side][3]};
+  for (int i = 0; i < 6; ++i) {
+    cuuint64_t dims[2] = {(cuuint64_t)g.W, (cuuint64_t)vis_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)g.pitch * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)sx, (cuuint32_t)sy};
+    cuuint32_t estr[2] = {1, 1};
+    void* base = bases[i] + (size_t)first_row * g.pitch;
+    CUresult r = enc(&out->m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+      return cudaErrorInvalidValue;
+    }
+  }
+  return cudaSuccess;
+}
+
+// ---- unfused launchers -------------------------------------------------------------------
+cudaError_t launch_unfused_update(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st) {
+  if (lr1 <= lr0) return cudaSuccess;
+  const size_t off = (size_t)TWS_HALO_ROWS * g.pitch;
+  dim3 block(128), grid((g.pitch / 4 + 127) / 128, (lr1 - lr0) < 65535 ? (lr1 - lr0) : 65535);
+  unfused_update_kernel<<<grid, block, 0, st>>>(g, p.h + off, p.d[side] + off, p.F[side][0] + off, p.F[side][1] + off,
+                                                 p.F[side][2] + off, p.F[side][3] + off, c, lr0, lr1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unfused_apply(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st) {
+  if (lr1 <= lr0) return cudaSuccess;
+  const size_t off = (size_t)TWS_HALO_ROWS * g.pitch;
+  dim3 block(128), grid((g.pitch / 4 + 127) / 128, (lr1 - lr0) < 65535 ? (lr1 - lr0) : 65535);
+  unfused_apply_kernel<<<grid, block, 0, st>>>(g, p.d[side] + off, p.F[side][0] + off, p.F[side][1] + off, p.F[side][2] + off,
+                                                p.F[side][3] + off, p.v + off, c, lr0, lr1);
+  return cudaGetLastError();
+}
+
+}  // namespace tws

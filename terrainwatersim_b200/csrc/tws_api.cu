@@ -1,0 +1,691 @@
+// tws_api.cu — host side of libtws.so: the C ABI of include/tws.h.
+// Mirrors the simulation half of the reference's `Terrain` class (Terrain.cpp:150-277):
+// parameter derivation, create/reset, inject, the step loop and the frame accumulator.
+// No arithmetic on simulation state happens on the host; there is no CPU fallback.
+#include "tws_internal.h"
+
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+using namespace tws;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Peer {
+  bool present = false;
+  bool ipc = false;          // opened with cudaIpcOpenMemHandle (must be closed)
+  uint8_t* slab = nullptr;   // peer slab base, addressable from this device
+  int rows = 0;              // peer's own rows
+  Planes planes{};
+  Control* ctrl = nullptr;
+};
+
+}  // namespace
+
+struct tws_sim {
+  tws_params prm{};
+  Geom geom{};
+  StepConsts consts{};
+  double step_length = 0.0;          // m_simulationStepLength (ezTime, double seconds)
+  double accumulator = 0.0;          // m_timeSinceLastSimulationStep
+  uint8_t* slab = nullptr;
+  size_t slab_bytes = 0;
+  size_t plane_elems = 0;
+  Planes planes{};
+  Control* ctrl = nullptr;
+  int cur = 0;                       // ping-pong side holding the current d / F
+  int K = 1;                         // steps per launch
+  TmaSet tma[TWS_MAX_TB + 1][2];     // [k][side]
+  bool tma_ready[TWS_MAX_TB + 1] = {};
+  cudaStream_t st_main = nullptr, st_edge = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_main = nullptr, ev_edge = nullptr;
+  bool timed = false;
+  uint64_t launches = 0;
+  uint32_t epoch = 0;                // exchange blocks completed (same on all strips)
+  Peer up, down;
+  bool connected = false;
+  float* white_dev = nullptr;        // 4096-entry noise table
+  double* partials = nullptr;        // volume partial sums (device)
+  float* staging = nullptr;          // AoS staging for flux / terrain-info transfers
+  size_t staging_bytes = 0;
+  void* packed_info = nullptr;       // publish buffers
+  void* packed_flow = nullptr;
+  std::string err;
+};
+
+namespace {
+
+constexpr int kVolumeBlocks = 1024;
+
+tws_status fail(tws_sim* s, tws_status code, const std::string& msg) {
+  if (s) s->err = msg; else g_create_error = msg;
+  return code;
+}
+tws_status cuda_fail(tws_sim* s, cudaError_t e, const char* what) {
+  return fail(s, e == cudaErrorMemoryAllocation ? TWS_ERR_NOMEM : TWS_ERR_CUDA,
+              std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+#define TWS_CUDA(s, call)                                        \
+  do {                                                           \
+    cudaError_t e__ = (call);                                    \
+    if (e__ != cudaSuccess) return cuda_fail((s), e__, #call);   \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Slab layout is a pure function of (width, rows) so a peer can address our planes.
+void layout_planes(uint8_t* base, int pitch, int rows, Planes* p, size_t* plane_elems, size_t* total) {
+  const size_t elems = (size_t)pitch * (size_t)(rows + 2 * TWS_HALO_ROWS);
+  const size_t pb = align_up(elems * sizeof(float), 1024);
+  size_t off = TWS_CTRL_BYTES;
+  auto take = [&]() { uint8_t* q = base ? base + off : nullptr; off += pb; return q; };
+  p->h = (float*)take();
+  p->d[0] = (float*)take();
+  p->d[1] = (float*)take();
+  for (int s = 0; s < 2; ++s)
+    for (int i = 0; i < 4; ++i) p->F[s][i] = (float*)take();
+  p->v = (uint32_t*)take();
+  if (plane_elems) *plane_elems = elems;
+  if (total) *total = off;
+}
+
+int pitch_for(int width) { return (int)align_up((size_t)width, 64); }
+
+// Terrain.cpp:175-198 — see tws_step_constants in tws.h.
+void derive_constants(tws_sim* s) {
+  const tws_params& p = s->prm;
+  s->step_length = (double)(1.0f / p.steps_per_second);                   // ezTime::Seconds(1.0f / sps)
+  const float cell = p.world_size / (float)p.width;                       // float / uint -> float
+  s->consts.friction = powf(p.flow_damping, (float)s->step_length);       // ezMath::Pow == powf
+  s->consts.accel = (float)(s->step_length * p.flow_acceleration * cell); // double product
+  s->consts.area_inv = (float)(s->step_length / (cell * cell));
+  s->consts.rain_step = (float)(s->step_length * p.rain_rate);            // EXT
+  s->consts.evap_step = (float)(s->step_length * p.evaporation_rate);     // EXT
+  s->consts.ext_sources = (s->consts.rain_step != 0.0f || s->consts.evap_step != 0.0f) ? 1 : 0;
+  s->consts.closed = (p.boundary == TWS_BOUNDARY_CLOSED) ? 1 : 0;
+}
+
+bool bad_float(float v) { return !(v == v) || std::isinf(v); }
+
+tws_status ensure_tma(tws_sim* s, int k) {
+  if (s->tma_ready[k]) return TWS_OK;
+  for (int side = 0; side < 2; ++side) {
+    std::string e;
+    cudaError_t r = fused_build_tma(k, s->geom, s->planes, side, &s->tma[k][side], &e);
+    if (r != cudaSuccess) return fail(s, TWS_ERR_CUDA, e.empty() ? std::string("building TMA descriptors failed") : e);
+  }
+  s->tma_ready[k] = true;
+  return TWS_OK;
+}
+
+tws_status ensure_staging(tws_sim* s, size_t bytes) {
+  if (s->staging_bytes >= bytes) return TWS_OK;
+  if (s->staging) cudaFree(s->staging);
+  s->staging = nullptr; s->staging_bytes = 0;
+  TWS_CUDA(s, cudaMalloc(&s->staging, bytes));
+  s->staging_bytes = bytes;
+  return TWS_OK;
+}
+
+size_t field_elem_bytes(tws_field f) {
+  switch (f) {
+    case TWS_FIELD_TERRAIN: case TWS_FIELD_WATER: return 4;
+    case TWS_FIELD_FLUX: case TWS_FIELD_TERRAIN_INFO: return 16;
+    case TWS_FIELD_VELOCITY: return 4;
+  }
+  return 0;
+}
+
+// Push `nrows` edge rows of the given side (d + 4 flux planes, optionally h) into the
+// neighbours' halo rows.  Returns the number of kernels launched.
+tws_status push_edges(tws_sim* s, int side, bool with_h, cudaStream_t st) {
+  RowCopy c[2]; int n = 0;
+  const int P = TWS_HALO_ROWS;
+  auto fill = [&](const Peer& peer, bool to_up) {
+    RowCopy r{};
+    int k = 0;
+    r.src[k] = s->planes.d[side]; r.dst[k] = peer.planes.d[side]; ++k;
+    for (int i = 0; i < 4; ++i) { r.src[k] = s->planes.F[side][i]; r.dst[k] = peer.planes.F[side][i]; ++k; }
+    if (with_h) { r.src[k] = s->planes.h; r.dst[k] = peer.planes.h; ++k; }
+    r.nplanes = k; r.nrows = P; r.pitch = s->geom.pitch;
+    if (to_up) { r.src_row = TWS_HALO_ROWS; r.dst_row = TWS_HALO_ROWS + peer.rows; }          // my top rows -> its bottom halo
+    else { r.src_row = TWS_HALO_ROWS + s->geom.rows - P; r.dst_row = TWS_HALO_ROWS - P; }      // my bottom rows -> its top halo
+    return r;
+  };
+  if (s->up.present) c[n++] = fill(s->up, true);
+  if (s->down.present) c[n++] = fill(s->down, false);
+  if (n == 0) return TWS_OK;
+  TWS_CUDA(s, launch_row_copy(c[0], c[n - 1], n, st));
+  s->launches += 1;
+  return TWS_OK;
+}
+
+tws_status post_and_count(tws_sim* s, cudaStream_t st) {
+  s->epoch += 1;
+  volatile uint32_t* uf = s->up.present ? &s->up.ctrl->flag_from_down : nullptr;
+  volatile uint32_t* df = s->down.present ? &s->down.ctrl->flag_from_up : nullptr;
+  if (uf || df) {
+    TWS_CUDA(s, launch_post_flags(uf, df, s->epoch, st));
+    s->launches += 1;
+  }
+  return TWS_OK;
+}
+
+// One block of k fused steps (or one unfused step) including the strip exchange.
+tws_status run_block(tws_sim* s, int k) {
+  const Geom& g = s->geom;
+  const bool strip = g.has_up || g.has_down;
+  const int src = s->cur;
+  if (s->prm.backend == TWS_BACKEND_UNFUSED) {
+    TWS_CUDA(s, launch_unfused_update(g, s->planes, src, s->consts, 0, g.rows, s->st_main));
+    TWS_CUDA(s, launch_unfused_apply(g, s->planes, src, s->consts, 0, g.rows, s->st_main));
+    s->launches += 2;
+    return TWS_OK;
+  }
+  tws_status r = ensure_tma(s, k);
+  if (r) return r;
+  const int tiles = fused_tile_rows(k, g.rows);
+  if (!strip) {
+    TWS_CUDA(s, launch_fused(k, g, s->planes, s->tma[k][src], src, s->consts, 0, tiles, s->st_main));
+    s->launches += 1;
+    s->cur = 1 - src;
+    return TWS_OK;
+  }
+  // Strip: tile rows whose outputs depend on a halo, or that the neighbour needs pushed,
+  // run on the edge stream after the neighbours' flags; the interior does not wait.
+  const int oy = fused_out_rows_per_tile(k);
+  const int need = TWS_HALO_ROWS;                       // rows pushed / rows depending on the halo (>= 2k)
+  int e_top = g.has_up ? (need + oy - 1) / oy : 0;
+  int e_bot = g.has_down ? (need + oy - 1) / oy : 0;
+  if (e_top + e_bot >= tiles) { e_top = tiles; e_bot = 0; }
+  const int i0 = e_top, i1 = tiles - e_bot;
+  // interior (main stream) — ordered after the previous block's edge work
+  TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));
+  if (i1 > i0) {
+    TWS_CUDA(s, launch_fused(k, g, s->planes, s->tma[k][src], src, s->consts, i0, i1, s->st_main));
+    s->launches += 1;
+  }
+  // edges (edge stream) — ordered after the previous block's interior
+  TWS_CUDA(s, cudaStreamWaitEvent(s->st_edge, s->ev_main, 0));
+  TWS_CUDA(s, launch_wait_flags(s->ctrl, g.has_up, g.has_down, s->epoch, s->st_edge)); s->launches++;
+  if (e_top > 0) { TWS_CUDA(s, launch_fused(k, g, s->planes, s->tma[k][src], src, s->consts, 0, e_top, s->st_edge)); s->launches++; }
+  if (e_bot > 0) { TWS_CUDA(s, launch_fused(k, g, s->planes, s->tma[k][src], src, s->consts, i1, tiles, s->st_edge)); s->launches++; }
+  r = push_edges(s, 1 - src, false, s->st_edge); if (r) return r;
+  r = post_and_count(s, s->st_edge); if (r) return r;
+  TWS_CUDA(s, cudaEventRecord(s->ev_edge, s->st_edge));
+  TWS_CUDA(s, cudaEventRecord(s->ev_main, s->st_main));
+  s->cur = 1 - src;
+  return TWS_OK;
+}
+
+tws_status run_steps(tws_sim* s, int n) {
+  const Geom& g = s->geom;
+  const bool strip = g.has_up || g.has_down;
+  if (strip && !s->connected) return fail(s, TWS_ERR_STATE, "strip sim stepped before tws_halo_connect");
+  TWS_CUDA(s, cudaEventRecord(s->ev_start, s->st_main));
+  const int K = (s->prm.backend == TWS_BACKEND_FUSED_TB) ? s->K : 1;
+  while (n > 0) {
+    const int k = std::min(n, K);
+    tws_status r = run_block(s, k);
+    if (r) return r;
+    n -= k;
+  }
+  if (strip) TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));
+  TWS_CUDA(s, cudaEventRecord(s->ev_stop, s->st_main));
+  s->timed = true;
+  return TWS_OK;
+}
+
+tws_status sync_all(tws_sim* s) {
+  TWS_CUDA(s, cudaStreamSynchronize(s->st_edge));
+  TWS_CUDA(s, cudaStreamSynchronize(s->st_main));
+  uint32_t e = 0;
+  TWS_CUDA(s, cudaMemcpy(&e, &s->ctrl->error, sizeof(e), cudaMemcpyDeviceToHost));
+  if (e) return fail(s, TWS_ERR_STATE, "halo exchange timed out waiting for a neighbouring strip");
+  return TWS_OK;
+}
+
+void close_peer(Peer& p) {
+  if (p.present && p.ipc && p.slab) cudaIpcCloseMemHandle(p.slab);
+  p = Peer{};
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tws_version(void) { return "tws-b200 0.1 (sm_100a)"; }
+int32_t tws_abi_version(void) { return TWS_ABI_VERSION; }
+
+void tws_default_params(tws_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->size = sizeof(tws_params);
+  p->width = 1024; p->height = 1024; p->row_begin = 0; p->row_end = 1024;      // Terrain.cpp:23
+  p->world_size = 1024.0f;                                                      // Terrain.cpp:22
+  p->steps_per_second = 60.0f; p->flow_damping = 0.98f; p->flow_acceleration = 10.0f;   // Terrain.cpp:28-30
+  p->boundary = TWS_BOUNDARY_REFERENCE_OPEN;
+  p->backend = TWS_BACKEND_FUSED;
+  p->temporal_block = 1;
+  p->device = 0;
+}
+
+const char* tws_last_error(const tws_sim* s) { return s ? s->err.c_str() : g_create_error.c_str(); }
+
+tws_status tws_create(const tws_params* p, tws_sim** out) {
+  if (out) *out = nullptr;
+  if (!p || !out) return fail(nullptr, TWS_ERR_INVALID, "tws_create: null argument");
+  if (p->size != sizeof(tws_params)) return fail(nullptr, TWS_ERR_INVALID, "tws_create: params.size does not match this ABI");
+  if (p->width < 1 || p->height < 1) return fail(nullptr, TWS_ERR_INVALID, "tws_create: width/height must be >= 1");
+  if (p->row_begin < 0 || p->row_end > p->height || p->row_end <= p->row_begin)
+    return fail(nullptr, TWS_ERR_INVALID, "tws_create: bad strip rows");
+  const bool strip = p->row_begin > 0 || p->row_end < p->height;
+  if (strip && p->backend == TWS_BACKEND_UNFUSED)
+    return fail(nullptr, TWS_ERR_UNSUPPORTED, "tws_create: the unfused baseline updates in place and cannot run on a strip; use a fused backend");
+  if (strip && p->row_end - p->row_begin < TWS_HALO_ROWS)
+    return fail(nullptr, TWS_ERR_INVALID, "tws_create: a strip needs at least 8 rows");
+  if (bad_float(p->world_size) || !(p->world_size > 0.0f)) return fail(nullptr, TWS_ERR_INVALID, "tws_create: world_size must be > 0");
+  if (bad_float(p->steps_per_second) || !(p->steps_per_second > 0.0f)) return fail(nullptr, TWS_ERR_INVALID, "tws_create: steps_per_second must be > 0");
+  if (bad_float(p->flow_damping) || p->flow_damping < 0.0f) return fail(nullptr, TWS_ERR_INVALID, "tws_create: flow_damping must be >= 0");
+  if (bad_float(p->flow_acceleration) || p->flow_acceleration < 0.0f) return fail(nullptr, TWS_ERR_INVALID, "tws_create: flow_acceleration must be >= 0");
+  if (bad_float(p->rain_rate) || bad_float(p->evaporation_rate) || p->rain_rate < 0.0f || p->evaporation_rate < 0.0f)
+    return fail(nullptr, TWS_ERR_INVALID, "tws_create: rain/evaporation must be >= 0");
+  if (p->backend < TWS_BACKEND_UNFUSED || p->backend > TWS_BACKEND_FUSED_TB) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown backend");
+  if (p->boundary != TWS_BOUNDARY_REFERENCE_OPEN && p->boundary != TWS_BOUNDARY_CLOSED) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown boundary");
+  if (p->backend == TWS_BACKEND_FUSED_TB && (p->temporal_block < 1 || p->temporal_block > TWS_MAX_TB))
+    return fail(nullptr, TWS_ERR_INVALID, "tws_create: temporal_block must be 1..4");
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, TWS_ERR_CUDA, std::string("tws_create: no CUDA device (") + cudaGetErrorString(e) + "); libtws has no CPU path");
+  if (p->device < 0 || p->device >= ndev) return fail(nullptr, TWS_ERR_INVALID, "tws_create: device ordinal out of range");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, p->device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major != 10) return fail(nullptr, TWS_ERR_CUDA, "tws_create: device is not sm_100 (kernels are built for sm_100a only)");
+
+  tws_sim* s = new (std::nothrow) tws_sim;
+  if (!s) return fail(nullptr, TWS_ERR_NOMEM, "tws_create: out of host memory");
+  s->prm = *p;
+  s->K = (p->backend == TWS_BACKEND_FUSED_TB) ? p->temporal_block : 1;
+  DeviceGuard guard(p->device);
+  Geom& g = s->geom;
+  g.W = p->width; g.Hg = p->height; g.row0 = p->row_begin; g.rows = p->row_end - p->row_begin;
+  g.pitch = pitch_for(p->width);
+  g.has_up = p->row_begin > 0; g.has_down = p->row_end < p->height;
+  derive_constants(s);
+  layout_planes(nullptr, g.pitch, g.rows, &s->planes, &s->plane_elems, &s->slab_bytes);
+  tws_status rc = TWS_OK;
+  auto bail = [&](tws_status code, const std::string& msg) { g_create_error = msg; tws_destroy(s); return code; };
+  if ((e = cudaMalloc(&s->slab, s->slab_bytes)) != cudaSuccess)
+    return bail(e == cudaErrorMemoryAllocation ? TWS_ERR_NOMEM : TWS_ERR_CUDA, std::string("tws_create: cudaMalloc of the state slab failed: ") + cudaGetErrorString(e));
+  layout_planes(s->slab, g.pitch, g.rows, &s->planes, nullptr, nullptr);
+  s->ctrl = (Control*)s->slab;
+  if ((e = cudaStreamCreateWithFlags(&s->st_main, cudaStreamNonBlocking)) != cudaSuccess) return bail(TWS_ERR_CUDA, cudaGetErrorString(e));
+  int lo_prio = 0, hi_prio = 0;
+  cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+  if ((e = cudaStreamCreateWithPriority(&s->st_edge, cudaStreamNonBlocking, hi_prio)) != cudaSuccess) return bail(TWS_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaEventCreate(&s->ev_start)) != cudaSuccess || (e = cudaEventCreate(&s->ev_stop)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&s->ev_main, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&s->ev_edge, cudaEventDisableTiming)) != cudaSuccess)
+    return bail(TWS_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMemsetAsync(s->slab, 0, s->slab_bytes, s->st_main)) != cudaSuccess) return bail(TWS_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaMalloc(&s->partials, kVolumeBlocks * sizeof(double))) != cudaSuccess) return bail(TWS_ERR_NOMEM, cudaGetErrorString(e));
+  if ((e = cudaEventRecord(s->ev_main, s->st_main)) != cudaSuccess || (e = cudaEventRecord(s->ev_edge, s->st_edge)) != cudaSuccess)
+    return bail(TWS_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaStreamSynchronize(s->st_main)) != cudaSuccess) return bail(TWS_ERR_CUDA, cudaGetErrorString(e));
+  (void)rc;
+  *out = s;
+  return TWS_OK;
+}
+
+tws_status tws_destroy(tws_sim* s) {
+  if (!s) return TWS_OK;
+  DeviceGuard guard(s->prm.device);
+  if (s->st_main) cudaStreamSynchronize(s->st_main);
+  if (s->st_edge) cudaStreamSynchronize(s->st_edge);
+  close_peer(s->up); close_peer(s->down);
+  if (s->staging) cudaFree(s->staging);
+  if (s->partials) cudaFree(s->partials);
+  if (s->white_dev) cudaFree(s->white_dev);
+  if (s->packed_info) cudaFree(s->packed_info);
+  if (s->packed_flow) cudaFree(s->packed_flow);
+  if (s->slab) cudaFree(s->slab);
+  if (s->ev_start) cudaEventDestroy(s->ev_start);
+  if (s->ev_stop) cudaEventDestroy(s->ev_stop);
+  if (s->ev_main) cudaEventDestroy(s->ev_main);
+  if (s->ev_edge) cudaEventDestroy(s->ev_edge);
+  if (s->st_main) cudaStreamDestroy(s->st_main);
+  if (s->st_edge) cudaStreamDestroy(s->st_edge);
+  delete s;
+  return TWS_OK;
+}
+
+tws_status tws_set_steps_per_second(tws_sim* s, float v) {
+  if (!s) return TWS_ERR_INVALID;
+  if (bad_float(v) || !(v > 0.0f)) return fail(s, TWS_ERR_INVALID, "steps_per_second must be > 0");
+  s->prm.steps_per_second = v; derive_constants(s);          // Terrain.cpp:175-185 resets all three
+  return TWS_OK;
+}
+tws_status tws_set_flow_damping(tws_sim* s, float v) {
+  if (!s) return TWS_ERR_INVALID;
+  if (bad_float(v) || v < 0.0f) return fail(s, TWS_ERR_INVALID, "flow_damping must be >= 0");
+  s->prm.flow_damping = v; derive_constants(s);
+  return TWS_OK;
+}
+tws_status tws_set_flow_acceleration(tws_sim* s, float v) {
+  if (!s) return TWS_ERR_INVALID;
+  if (bad_float(v) || v < 0.0f) return fail(s, TWS_ERR_INVALID, "flow_acceleration must be >= 0");
+  s->prm.flow_acceleration = v; derive_constants(s);
+  return TWS_OK;
+}
+tws_status tws_set_sources(tws_sim* s, float rain, float evap) {
+  if (!s) return TWS_ERR_INVALID;
+  if (bad_float(rain) || bad_float(evap) || rain < 0.0f || evap < 0.0f) return fail(s, TWS_ERR_INVALID, "rain/evaporation must be >= 0");
+  s->prm.rain_rate = rain; s->prm.evaporation_rate = evap; derive_constants(s);
+  return TWS_OK;
+}
+tws_status tws_get_step_constants(const tws_sim* s, tws_step_constants* out) {
+  if (!s || !out) return TWS_ERR_INVALID;
+  out->flow_friction_per_step = s->consts.friction;
+  out->water_acceleration_per_step = s->consts.accel;
+  out->cell_area_inv_time_scaled = s->consts.area_inv;
+  return TWS_OK;
+}
+
+static tws_status transfer(tws_sim* s, tws_field field, void* host, size_t bytes, bool upload) {
+  if (!s) return TWS_ERR_INVALID;
+  if (!host) return fail(s, TWS_ERR_INVALID, "null host buffer");
+  const size_t eb = field_elem_bytes(field);
+  if (eb == 0) return fail(s, TWS_ERR_INVALID, "unknown field");
+  const Geom& g = s->geom;
+  const size_t want = (size_t)g.W * g.rows * eb;
+  if (bytes != want) return fail(s, TWS_ERR_INVALID, "host buffer size does not match the field (expected " + std::to_string(want) + " bytes)");
+  if (upload && field == TWS_FIELD_VELOCITY) return fail(s, TWS_ERR_INVALID, "velocity is an output (m_waterFlowMap is write-only in the reference)");
+  DeviceGuard guard(s->prm.device);
+  tws_status r = sync_all(s);
+  if (r) return r;
+  const size_t off = (size_t)TWS_HALO_ROWS * g.pitch;
+  if (field == TWS_FIELD_TERRAIN || field == TWS_FIELD_WATER || field == TWS_FIELD_VELOCITY) {
+    void* plane = field == TWS_FIELD_TERRAIN ? (void*)(s->planes.h + off)
+                : field == TWS_FIELD_WATER   ? (void*)(s->planes.d[s->cur] + off)
+                                             : (void*)(s->planes.v + off);
+    if (upload) TWS_CUDA(s, cudaMemcpy2DAsync(plane, (size_t)g.pitch * 4, host, (size_t)g.W * 4, (size_t)g.W * 4, g.rows, cudaMemcpyHostToDevice, s->st_main));
+    else TWS_CUDA(s, cudaMemcpy2DAsync(host, (size_t)g.W * 4, plane, (size_t)g.pitch * 4, (size_t)g.W * 4, g.rows, cudaMemcpyDeviceToHost, s->st_main));
+    TWS_CUDA(s, cudaStreamSynchronize(s->st_main));
+    return TWS_OK;
+  }
+  // AoS fields go through a device staging buffer in row chunks (<= 64 MiB).
+  const size_t row_bytes = (size_t)g.W * 16;
+  int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)g.rows, ((size_t)64 << 20) / row_bytes));
+  r = ensure_staging(s, (size_t)chunk * row_bytes);
+  if (r) return r;
+  for (int r0 = 0; r0 < g.rows; r0 += chunk) {
+    const int n = std::min(chunk, g.rows - r0);
+    uint8_t* hp = (uint8_t*)host + (size_t)r0 * row_bytes;
+    if (upload) TWS_CUDA(s, cudaMemcpyAsync(s->staging, hp, (size_t)n * row_bytes, cudaMemcpyHostToDevice, s->st_main));
+    if (field == TWS_FIELD_FLUX) TWS_CUDA(s, launch_pack_flux(g, s->planes, s->cur, s->staging, r0, n, !upload, s->st_main));
+    else TWS_CUDA(s, launch_pack_info(g, s->planes, s->cur, s->staging, r0, n, !upload, s->st_main));
+    s->launches += 1;
+    if (!upload) TWS_CUDA(s, cudaMemcpyAsync(hp, s->staging, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, s->st_main));
+    TWS_CUDA(s, cudaStreamSynchronize(s->st_main));
+  }
+  return TWS_OK;
+}
+
+tws_status tws_upload(tws_sim* s, tws_field field, const void* host, size_t bytes) { return transfer(s, field, (void*)host, bytes, true); }
+tws_status tws_readback(tws_sim* s, tws_field field, void* host, size_t bytes) { return transfer(s, field, host, bytes, false); }
+
+// Random.cpp:22-58 + NoiseGenerator.cpp:6-10: the 4096-entry table, generated on the host
+// (a 4096-step sequential recurrence), everything per-cell runs on the GPU.
+static void white_noise_table(uint32_t seed, float* out) {
+  const int N = 624, M = 397;
+  std::vector<uint32_t> mt(N);
+  for (int i = 0; i < N; ++i) mt[i] = (i % 2) ? (seed + (uint32_t)i * 527u) : ((2135u + seed * 74111u) * (uint32_t)i);
+  auto twist = [&](int i) {
+    const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1 == N) ? 0 : i + 1] & 0x7fffffffu);
+    mt[i] = mt[(i + M) % N] ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+  };
+  for (int i = 0; i < N; ++i) twist(i);
+  int idx = 0;
+  for (int k = 0; k < 4096; ++k) {
+    twist(idx);
+    uint32_t y = mt[idx];
+    idx = (idx + 1 == N) ? 0 : idx + 1;
+    y ^= y >> 11; y ^= (y << 7) & 0x9D2C5680u; y ^= (y << 15) & 0xEFC60000u; y ^= y >> 18;
+    out[k] = (float)(y * 4.656612874e-10 - 1.0);
+  }
+}
+
+tws_status tws_reset_reference_scene(tws_sim* s, uint32_t seed, float height_scale, int32_t lo, int32_t hi, float persistence) {
+  if (!s) return TWS_ERR_INVALID;
+  if (lo < 0 || hi < lo || hi > 24) return fail(s, TWS_ERR_INVALID, "octave range must satisfy 0 <= lo <= hi <= 24");
+  if (bad_float(height_scale) || bad_float(persistence)) return fail(s, TWS_ERR_INVALID, "height_scale/persistence must be finite");
+  if (s->geom.W < 2 || s->geom.Hg < 2) return fail(s, TWS_ERR_INVALID, "reference scene needs a grid of at least 2x2");
+  DeviceGuard guard(s->prm.device);
+  tws_status r = sync_all(s);
+  if (r) return r;
+  if (!s->white_dev) TWS_CUDA(s, cudaMalloc(&s->white_dev, 4096 * sizeof(float)));
+  float table[4096];
+  white_noise_table(seed, table);
+  TWS_CUDA(s, cudaMemcpyAsync(s->white_dev, table, sizeof(table), cudaMemcpyHostToDevice, s->st_main));
+  // flux = 0 (Terrain.cpp:230-234), both sides, halos included; depth/terrain regenerated.
+  for (int side = 0; side < 2; ++side)
+    for (int i = 0; i < 4; ++i) TWS_CUDA(s, cudaMemsetAsync(s->planes.F[side][i], 0, s->plane_elems * sizeof(float), s->st_main));
+  TWS_CUDA(s, launch_scene(s->geom, s->planes, s->cur, s->white_dev, height_scale, lo, hi, persistence, s->st_main));
+  s->launches += 1;
+  s->accumulator = 0.0;
+  TWS_CUDA(s, cudaStreamSynchronize(s->st_main));
+  return TWS_OK;
+}
+
+tws_status tws_inject_brush(tws_sim* s, float cx, float cy, float intensity, float size_sq) {
+  if (!s) return TWS_ERR_INVALID;
+  if (bad_float(cx) || bad_float(cy) || bad_float(intensity)) return fail(s, TWS_ERR_INVALID, "brush centre/intensity must be finite");
+  if (bad_float(size_sq) || !(size_sq > 0.0f)) return fail(s, TWS_ERR_INVALID, "brush size_sq must be > 0");
+  DeviceGuard guard(s->prm.device);
+  const bool strip = s->geom.has_up || s->geom.has_down;
+  if (strip) TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));
+  int launched = 0;
+  TWS_CUDA(s, launch_brush(s->geom, s->planes.d[s->cur] + (size_t)TWS_HALO_ROWS * s->geom.pitch, cx, cy, intensity, size_sq, s->st_main, &launched));
+  s->launches += launched;
+  if (strip) { TWS_CUDA(s, cudaEventRecord(s->ev_main, s->st_main)); }
+  return TWS_OK;
+}
+
+tws_status tws_inject_brush_world(tws_sim* s, float wx, float wz, float strength) {
+  if (!s) return TWS_ERR_INVALID;
+  if (bad_float(wx) || bad_float(wz)) return fail(s, TWS_ERR_INVALID, "brush position must be finite");
+  // Terrain.cpp:152-155: pos /= worldSize; Fraction(); pos *= (float)resolution.  The
+  // reference grid is square; for width != height each axis scales by its own resolution.
+  float px = wx / s->prm.world_size, pz = wz / s->prm.world_size;
+  px = px - truncf(px); pz = pz - truncf(pz);
+  px *= (float)s->prm.width; pz *= (float)s->prm.height;
+  return tws_inject_brush(s, px, pz, strength, 32.0f);                                // Terrain.cpp:159
+}
+
+tws_status tws_step(tws_sim* s, int32_t n) {
+  if (!s) return TWS_ERR_INVALID;
+  if (n < 0) return fail(s, TWS_ERR_INVALID, "tws_step: n must be >= 0");
+  DeviceGuard guard(s->prm.device);
+  return run_steps(s, n);
+}
+
+tws_status tws_advance(tws_sim* s, double frame_seconds, uint32_t* steps_done) {
+  if (steps_done) *steps_done = 0;
+  if (!s) return TWS_ERR_INVALID;
+  if (!(frame_seconds >= 0.0) || std::isinf(frame_seconds)) return fail(s, TWS_ERR_INVALID, "tws_advance: frame time must be finite and >= 0");
+  s->accumulator += frame_seconds;                                                    // Terrain.cpp:242
+  uint32_t n = (uint32_t)(s->accumulator / s->step_length);                           // :243
+  s->accumulator -= s->step_length * n;                                               // :244
+  n = std::min<uint32_t>(n, 10u);                                                     // :247
+  if (steps_done) *steps_done = n;
+  if (n == 0) return TWS_OK;
+  DeviceGuard guard(s->prm.device);
+  return run_steps(s, (int)n);
+}
+
+tws_status tws_total_volume(tws_sim* s, double* volume) {
+  if (!s || !volume) return TWS_ERR_INVALID;
+  DeviceGuard guard(s->prm.device);
+  tws_status r = sync_all(s);
+  if (r) return r;
+  TWS_CUDA(s, launch_volume(s->geom, s->planes.d[s->cur], s->partials, kVolumeBlocks, s->st_main));
+  s->launches += 1;
+  std::vector<double> h(kVolumeBlocks);
+  TWS_CUDA(s, cudaMemcpyAsync(h.data(), s->partials, kVolumeBlocks * sizeof(double), cudaMemcpyDeviceToHost, s->st_main));
+  TWS_CUDA(s, cudaStreamSynchronize(s->st_main));
+  double acc = 0.0;
+  for (double v : h) acc += v;
+  *volume = acc;
+  return TWS_OK;
+}
+
+tws_status tws_sync(tws_sim* s) {
+  if (!s) return TWS_ERR_INVALID;
+  DeviceGuard guard(s->prm.device);
+  return sync_all(s);
+}
+
+tws_status tws_elapsed_ms(tws_sim* s, float* ms) {
+  if (!s || !ms) return TWS_ERR_INVALID;
+  if (!s->timed) return fail(s, TWS_ERR_STATE, "no step batch has been timed yet");
+  DeviceGuard guard(s->prm.device);
+  TWS_CUDA(s, cudaEventSynchronize(s->ev_stop));
+  TWS_CUDA(s, cudaEventElapsedTime(ms, s->ev_start, s->ev_stop));
+  return TWS_OK;
+}
+
+uint64_t tws_kernel_launches(const tws_sim* s) { return s ? s->launches : 0; }
+
+tws_status tws_device_view(tws_sim* s, tws_field field, void** ptr, int64_t* pitch) {
+  if (!s || !ptr || !pitch) return TWS_ERR_INVALID;
+  const size_t off = (size_t)TWS_HALO_ROWS * s->geom.pitch;
+  switch (field) {
+    case TWS_FIELD_TERRAIN: *ptr = s->planes.h + off; break;
+    case TWS_FIELD_WATER: *ptr = s->planes.d[s->cur] + off; break;
+    case TWS_FIELD_VELOCITY: *ptr = s->planes.v + off; break;
+    default: return fail(s, TWS_ERR_INVALID, "tws_device_view: only TERRAIN, WATER and VELOCITY are single planes");
+  }
+  *pitch = s->geom.pitch;
+  return TWS_OK;
+}
+
+// ---- strips ---------------------------------------------------------------------------------
+tws_status tws_halo_export(tws_sim* s, tws_halo_handle* out) {
+  if (!s || !out) return TWS_ERR_INVALID;
+  DeviceGuard guard(s->prm.device);
+  std::memset(out, 0, sizeof(*out));
+  static_assert(sizeof(cudaIpcMemHandle_t) <= TWS_IPC_HANDLE_BYTES, "IPC handle does not fit");
+  cudaIpcMemHandle_t h;
+  TWS_CUDA(s, cudaIpcGetMemHandle(&h, s->slab));
+  std::memcpy(out->mem, &h, sizeof(h));
+  out->slab_bytes = s->slab_bytes;
+  out->row_begin = s->prm.row_begin; out->row_end = s->prm.row_end;
+  out->device = s->prm.device;
+  out->pid = (int32_t)getpid();
+  out->local_ptr = (uint64_t)(uintptr_t)s->slab;
+  return TWS_OK;
+}
+
+static tws_status open_peer(tws_sim* s, const tws_halo_handle* h, Peer* p, bool is_up) {
+  close_peer(*p);
+  if (!h) return TWS_OK;
+  const int rows = h->row_end - h->row_begin;
+  if (is_up ? (h->row_end != s->prm.row_begin) : (h->row_begin != s->prm.row_end))
+    return fail(s, TWS_ERR_INVALID, "tws_halo_connect: neighbour strip is not adjacent");
+  Planes pl; size_t total = 0;
+  layout_planes(nullptr, s->geom.pitch, rows, &pl, nullptr, &total);
+  if (total != h->slab_bytes) return fail(s, TWS_ERR_INVALID, "tws_halo_connect: neighbour slab layout mismatch (different width?)");
+  uint8_t* base = nullptr;
+  if (h->pid == (int32_t)getpid()) {
+    if (h->device != s->prm.device) {
+      int can = 0;
+      TWS_CUDA(s, cudaDeviceCanAccessPeer(&can, s->prm.device, h->device));
+      if (!can) return fail(s, TWS_ERR_CUDA, "tws_halo_connect: no peer access between the two devices");
+      cudaError_t e = cudaDeviceEnablePeerAccess(h->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(s, e, "cudaDeviceEnablePeerAccess");
+      (void)cudaGetLastError();
+    }
+    base = (uint8_t*)(uintptr_t)h->local_ptr;
+  } else {
+    cudaIpcMemHandle_t mh;
+    std::memcpy(&mh, h->mem, sizeof(mh));
+    void* ptr = nullptr;
+    TWS_CUDA(s, cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+    base = (uint8_t*)ptr;
+    p->ipc = true;
+  }
+  p->present = true; p->slab = base; p->rows = rows;
+  layout_planes(base, s->geom.pitch, rows, &p->planes, nullptr, nullptr);
+  p->ctrl = (Control*)base;
+  return TWS_OK;
+}
+
+tws_status tws_halo_connect(tws_sim* s, const tws_halo_handle* up, const tws_halo_handle* down) {
+  if (!s) return TWS_ERR_INVALID;
+  if ((up != nullptr) != (s->geom.has_up != 0) || (down != nullptr) != (s->geom.has_down != 0))
+    return fail(s, TWS_ERR_INVALID, "tws_halo_connect: a handle is required exactly where the strip has a neighbour");
+  DeviceGuard guard(s->prm.device);
+  tws_status r = open_peer(s, up, &s->up, true);
+  if (r) return r;
+  r = open_peer(s, down, &s->down, false);
+  if (r) return r;
+  s->connected = true;
+  return TWS_OK;
+}
+
+tws_status tws_halo_refresh(tws_sim* s) {
+  if (!s) return TWS_ERR_INVALID;
+  const bool strip = s->geom.has_up || s->geom.has_down;
+  if (!strip) return TWS_OK;
+  if (!s->connected) return fail(s, TWS_ERR_STATE, "tws_halo_refresh before tws_halo_connect");
+  DeviceGuard guard(s->prm.device);
+  TWS_CUDA(s, cudaStreamWaitEvent(s->st_edge, s->ev_main, 0));
+  tws_status r = push_edges(s, s->cur, true, s->st_edge);
+  if (r) return r;
+  r = post_and_count(s, s->st_edge);
+  if (r) return r;
+  TWS_CUDA(s, cudaEventRecord(s->ev_edge, s->st_edge));
+  return TWS_OK;
+}
+
+// ---- renderer hand-off -------------------------------------------------------------------------
+tws_status tws_publish_packed(tws_sim* s, void** info, void** flow) {
+  if (!s || !info || !flow) return TWS_ERR_INVALID;
+  DeviceGuard guard(s->prm.device);
+  const Geom& g = s->geom;
+  const size_t cells = (size_t)g.W * g.rows;
+  if (!s->packed_info) TWS_CUDA(s, cudaMalloc(&s->packed_info, cells * 16));
+  if (!s->packed_flow) TWS_CUDA(s, cudaMalloc(&s->packed_flow, cells * 4));
+  if (g.has_up || g.has_down) TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));
+  TWS_CUDA(s, launch_pack_info(g, s->planes, s->cur, (float*)s->packed_info, 0, g.rows, true, s->st_main));
+  s->launches += 1;
+  TWS_CUDA(s, cudaMemcpy2DAsync(s->packed_flow, (size_t)g.W * 4, s->planes.v + (size_t)TWS_HALO_ROWS * g.pitch, (size_t)g.pitch * 4,
+                                (size_t)g.W * 4, g.rows, cudaMemcpyDeviceToDevice, s->st_main));
+  *info = s->packed_info; *flow = s->packed_flow;
+  return TWS_OK;
+}
+
+#ifndef TWS_WITH_GL
+tws_status tws_gl_register(tws_sim* s, uint32_t, uint32_t) { return fail(s, TWS_ERR_UNSUPPORTED, "libtws was built without TWS_WITH_GL (no GL headers in this image)"); }
+tws_status tws_gl_publish(tws_sim* s) { return fail(s, TWS_ERR_UNSUPPORTED, "libtws was built without TWS_WITH_GL"); }
+tws_status tws_gl_unregister(tws_sim* s) { return fail(s, TWS_ERR_UNSUPPORTED, "libtws was built without TWS_WITH_GL"); }
+#endif
+
+}  // extern "C"

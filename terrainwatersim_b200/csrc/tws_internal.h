@@ -1,0 +1,90 @@
+// tws_internal.h — shared declarations of libtws.so (host side + kernel launchers).
+//
+// HBM layout.  Everything a strip owns lives in ONE cudaMalloc'ed slab so
+// a single CUDA-IPC handle exposes it to the neighbouring GPUs:
+//
+//   [ control block 4 KiB | h | d[0] | d[1] | F[0][+X,-X,+Y,-Y] | F[1][..] | v ]
+//
+// Every plane is planar fp32 (v: 2 x fp16 packed in 32 bit), `pitch` elements per row
+// (pitch = width rounded up to 64, pad columns always hold 0), `plane_rows` =
+// own rows + 2*TWS_HALO_ROWS rows; own local row r is plane row r + TWS_HALO_ROWS.
+// Halo rows mirror the neighbouring strip's edge rows (pushed over NVLink) or stay 0
+// and are never exposed to the kernels when the strip touches the global edge.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+
+#include "../../include/tws.h"
+
+#define TWS_HALO_ROWS 8          // 2 * max temporal block (4)
+#define TWS_MAX_TB 4
+#define TWS_CTRL_BYTES 4096
+
+namespace tws {
+
+// Control block at the start of the slab (device memory, written by peers).
+struct Control {
+  // Written by the strip ABOVE / BELOW (remote store over NVLink), polled locally.
+  alignas(128) volatile uint32_t flag_from_up;
+  alignas(128) volatile uint32_t flag_from_down;
+  alignas(128) uint32_t error;       // set by the wait kernel on timeout
+};
+
+struct StepConsts {
+  float friction, accel, area_inv;   // simulationCommon.glsl:1-13
+  float rain_step, evap_step;        // EXT, already multiplied by dt
+  int   closed;                      // EXT boundary
+  int   ext_sources;                 // rain_step != 0 || evap_step != 0
+};
+
+// Geometry handed to every kernel.
+struct Geom {
+  int W;            // global width
+  int Hg;           // global height
+  int row0;         // first global row of the strip
+  int rows;         // own rows
+  int pitch;        // elements per plane row
+  int has_up;       // halo rows above are live (a neighbour strip exists)
+  int has_down;
+};
+
+struct Planes {      // device pointers to plane row 0 (i.e. local row -TWS_HALO_ROWS)
+  float* h;
+  float* d[2];
+  float* F[2][4];
+  uint32_t* v;
+};
+
+// TMA descriptors of one ping-pong side: h, d, F x4 — boxes depend on the kernel config.
+struct TmaSet { CUtensorMap m[6]; };
+
+struct KernelStats { uint64_t launches = 0; };
+
+// ---- launchers (step_kernels.cu) ------------------------------------------------------
+// Fused K-level step over tile rows [ty0, ty1) of the strip; reads side `src`, writes 1-src.
+// Returns the number of tile rows for the strip through tiles_y when called with ty1 < 0.
+int  fused_tile_rows(int K, int rows);
+int  fused_out_rows_per_tile(int K);
+cudaError_t fused_build_tma(int K, const Geom& g, const Planes& p, int side, TmaSet* out, std::string* err);
+cudaError_t launch_fused(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c,
+                         int ty0, int ty1, cudaStream_t st);
+cudaError_t launch_unfused_update(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st);
+cudaError_t launch_unfused_apply(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st);
+
+// ---- launchers (aux_kernels.cu) -------------------------------------------------------
+cudaError_t launch_brush(const Geom& g, float* d, float cx, float cy, float intensity, float size_sq, cudaStream_t st, int* launched);
+cudaError_t launch_scene(const Geom& g, const Planes& p, int side, const float* white_dev, float height_scale, int lo, int hi,
+                         float persistence, cudaStream_t st);
+cudaError_t launch_pack_flux(const Geom& g, const Planes& p, int side, float* aos, int lr0, int nrows, bool to_aos, cudaStream_t st);
+cudaError_t launch_pack_info(const Geom& g, const Planes& p, int side, float* aos, int lr0, int nrows, bool to_aos, cudaStream_t st);
+cudaError_t launch_volume(const Geom& g, const float* d, double* partials, int nblocks, cudaStream_t st);
+// copy `nrows` plane rows of `nplanes` planes: dst[i] + dst_row*pitch <- src[i] + src_row*pitch
+struct RowCopy { const float* src[6]; float* dst[6]; int nplanes; int src_row; int dst_row; int nrows; int pitch; };
+cudaError_t launch_row_copy(const RowCopy& a, const RowCopy& b, int ncopies, cudaStream_t st);
+cudaError_t launch_post_flags(volatile uint32_t* up_flag, volatile uint32_t* down_flag, uint32_t value, cudaStream_t st);
+cudaError_t launch_wait_flags(Control* ctrl, int wait_up, int wait_down, uint32_t value, cudaStream_t st);
+
+}  // namespace tws
