@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — Gcell-updates/s of the shallow-water step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference ...                           # the reference's algorithm on the host cores
+    torchrun ... bench.py --gpus N ...                             # one rank per GPU (row strips)
+
+A "step" is one simulation step (flowUpdate + flowApply of the reference, Terrain.cpp:253-265)
+over the whole grid.  Workload: BASELINE config 3 — the reference scene generator
+(value-noise fBm terrain + central lake, seed 231656522) at 8192 x 8192 per GPU; at N GPUs the
+grid is 8192 x (8192*N), cut into N row strips (weak scaling), halo rows exchanged over NVLink
+by the library itself.  `--size S --strong` runs an S x S grid split over the ranks instead
+(BASELINE configs 4/5).  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+ALGO_BYTES_PER_CELL_UPDATE = 48          # R h4 + R d4 + R F16 + W d4 + W F16 + W v4
+HBM_FALLBACK_GBS = 6650.0                # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1200)
+    ap.add_argument("--warmup", type=int, default=60)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=8192, help="grid width (and per-GPU rows unless --strong)")
+    ap.add_argument("--strong", action="store_true", help="fixed size x size grid split over the ranks (strong scaling)")
+    ap.add_argument("--backend", default="tb", choices=["unfused", "fused", "tb"])
+    ap.add_argument("--tb", type=int, default=2, help="temporal block (steps per launch) for --backend tb")
+    ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the end-to-end leg (default min(steps, 40))")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verify-strips", action="store_true", help="compare the strips with a whole-grid run on rank 0 (small sizes)")
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_launch(kernel_tag: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, or None."""
+    p = ROOT / "profiles" / "traffic.json"
+    if not p.exists():
+        return None
+    try:
+        return json.loads(p.read_text()).get(kernel_tag)
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, device_index: int, period_s: float = 0.02):
+        super().__init__(daemon=True)
+        self.period = period_s
+        self.samples = []           # (t, sm_mhz, reasons_bitmask)
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self, t0: float, t1: float):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        note = None
+        if len(inside) < 3:
+            inside = self.samples
+            note = "timed region shorter than 3 samples: includes warm-up samples"
+        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+                 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        mask = 0
+        for s in inside:
+            mask |= s[2]
+        reasons = sorted(n for b, n in names.items() if mask & b and n != "gpu_idle")
+        out = {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(inside)}
+        if note:
+            out["note"] = note
+        return out
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores (the ONLY place bench.py uses oracle/)
+# --------------------------------------------------------------------------------------------------
+def cpu_oracle_throughput(size: int, steps: int, warmup: int, budget_s: float):
+    """Times the OpenMP oracle (bit-identical to the single-threaded one) on a bounded sample of
+    the workload: a `rows`-row slab of the size-wide reference scene, `rows` chosen so the whole
+    run fits the budget.  Returns (Gcell/s, cores, sample description, ms per step)."""
+    import numpy as np
+    from oracle.oracle_py import Oracle
+    o = Oracle(openmp=True)
+    cores = o.threads
+    consts = o.derive_consts(float(size), size)
+
+    scene = o.create_scene(size, size)
+
+    def slab(rows):                       # central rows: the lake sits in the middle of the map
+        a = (size - rows) // 2
+        return scene[a:a + rows].copy(), np.zeros((rows, size, 4), np.float32), np.zeros((rows, size, 2), np.float16)
+
+    # calibrate on a small slab
+    rows = min(size, 256)
+    t, f, v = slab(rows)
+    o.step(t, f, v, consts, 1)
+    t0 = time.perf_counter()
+    o.step(t, f, v, consts, 2)
+    per_row_step = (time.perf_counter() - t0) / 2 / rows
+    total_steps = max(1, steps + warmup)
+    rows_fit = int(budget_s / (per_row_step * total_steps))
+    rows = max(64, min(size, rows_fit // 64 * 64))
+    if rows != t.shape[0]:
+        t, f, v = slab(rows)
+    o.step(t, f, v, consts, warmup)
+    t0 = time.perf_counter()
+    o.step(t, f, v, consts, steps)
+    dt = time.perf_counter() - t0
+    gcells = rows * size * steps / dt / 1e9
+    sample = f"{size}x{rows} central-row slab of the {size}x{size} reference scene, {steps} steps after {warmup} warm-up, OpenMP oracle on {cores} threads"
+    return gcells, cores, sample, dt / steps * 1e3
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    val, cores, sample, ms = cpu_oracle_throughput(args.size, args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": "Gcell-updates/s per sim step (fp32)", "value": val, "unit": "Gcell-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, max(1, args.gpus)),
+        "cpu_baseline": {"value": val, "unit": "Gcell-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference has no CPU path and its GLSL cannot run here; this is the line-for-line C++ oracle port (oracle/tws_oracle.cpp), ms_per_step is for the sampled slab",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    W = args.size
+    Hg = args.size if args.strong else args.size * world
+    return {
+        "workload": f"{W}x{Hg} reference-scene fBm terrain (value noise octaves 2..10, persistence 0.43, seed 231656522) + central lake, "
+                    f"open (reference) boundary, no sources; BASELINE config {'4/5 (strong)' if args.strong else '3 per GPU'}",
+        "grid": [W, Hg], "backend": args.backend, "temporal_block": args.tb if args.backend == "tb" else 1,
+        "decomposition": f"{world} row strip(s), halo rows pushed over NVLink by the step kernels' stream (no collective)",
+        "l2": "state >= 3.2 GB per GPU, far larger than the 126 MB L2 (inputs larger than L2, no flush needed)",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("for --gpus N > 1 launch with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: terrainwatersim_b200 has no CPU path (use --impl reference for the host baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    import terrainwatersim_b200 as tws
+
+    W = args.size
+    Hg = args.size if args.strong else args.size * world
+    plan = tws.plan_strips(Hg, world)
+    backend = {"unfused": tws.BACKEND_UNFUSED, "fused": tws.BACKEND_FUSED, "tb": tws.BACKEND_FUSED_TB}[args.backend]
+    k = args.tb if args.backend == "tb" else 1
+    sim = tws.Terrain(W, height=Hg, rows=plan.rows(rank), backend=backend, temporal_block=k, device=local)
+    tws.connect_strips(sim, plan, rank)
+    sim.CreateHeightmapFromNoiseAndResetSim()
+    sim.sync()
+    cells_global = W * Hg
+    cells_local = W * sim.rows
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- device-resident throughput: warm-up, then exactly K steps ---------------------------------
+    barrier()
+    sim.step(args.warmup)
+    sim.sync()
+    barrier()
+    l0 = sim.kernel_launches()
+    t_wall0 = time.perf_counter()
+    sim.step(args.steps)
+    sim.sync()
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    ms_dev = sim.elapsed_ms()                  # CUDA events on the library's launching stream
+    launches_local = sim.kernel_launches() - l0
+    barrier()
+    sampler.stop()
+    ms = max_over_ranks(ms_dev)
+    launches = int(sum_over_ranks(float(launches_local)))
+    value = cells_global * args.steps / (ms * 1e-3) / 1e9
+    clocks = sampler.summary(t_wall0, t_wall1)
+
+    # ---- roofline of the dominant kernel (the step kernel; all launches in the region are it) -------
+    peak, peak_src = measured_peak_gbs()
+    if world == 1:
+        n_step_launches = launches_local
+    else:
+        n_step_launches = (args.steps + k - 1) // k      # per rank: interior launch count
+    launch_ms = ms_dev / max(1, (args.steps + k - 1) // k)
+    algo_bytes_per_launch = ALGO_BYTES_PER_CELL_UPDATE * cells_local * min(k, args.steps)
+    achieved = algo_bytes_per_launch / (launch_ms * 1e-3) / 1e9
+    tag = {"unfused": "unfused", "fused": "fused_k1", "tb": f"fused_k{k}"}[args.backend]
+    traffic = ncu_traffic_per_launch(tag) if (W == 8192 and sim.rows == 8192) else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "fused_step_kernel" if args.backend != "unfused" else "unfused_update_kernel+unfused_apply_kernel",
+                "peak_source": peak_src, "algorithmic_bytes_per_cell_update": ALGO_BYTES_PER_CELL_UPDATE,
+                "cell_updates_per_launch": cells_local * min(k, args.steps), "avg_launch_ms": launch_ms,
+                "note": "achieved = 48 B x cell-updates per launch / launch time; with temporal blocking (k steps per HBM round trip) real DRAM traffic is ~48/k B per cell-update, so frac may exceed 1"}
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        n_e2e = args.e2e_steps if args.e2e_steps > 0 else min(args.steps, 40)
+        d_host = torch.empty((sim.rows, W), dtype=torch.float32, pin_memory=True)
+        v_host = torch.empty((sim.rows, W, 2), dtype=torch.float16, pin_memory=True)
+        sim.readback_raw(tws.FIELD_WATER, d_host.data_ptr(), d_host.numel() * 4)
+        for _ in range(3):
+            sim.upload_raw(tws.FIELD_WATER, d_host.data_ptr(), d_host.numel() * 4)
+            sim.step(1)
+            sim.readback_raw(tws.FIELD_WATER, d_host.data_ptr(), d_host.numel() * 4)
+            sim.readback_raw(tws.FIELD_VELOCITY, v_host.data_ptr(), v_host.numel() * 2)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            # host-driven frame: the host owns the water layer (pinned), hands it to the library,
+            # runs one step and reads back the new water layer and the flow map.
+            sim.upload_raw(tws.FIELD_WATER, d_host.data_ptr(), d_host.numel() * 4)
+            if world > 1:
+                sim.halo_refresh()
+            sim.step(1)
+            sim.readback_raw(tws.FIELD_WATER, d_host.data_ptr(), d_host.numel() * 4)
+            sim.readback_raw(tws.FIELD_VELOCITY, v_host.data_ptr(), v_host.numel() * 2)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e = {"value": cells_global * n_e2e / dt / 1e9, "unit": "Gcell-updates/s", "h2d_bytes_per_step": int(sum_over_ranks(cells_local * 4.0)),
+               "d2h_bytes_per_step": int(sum_over_ranks(cells_local * 8.0)), "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
+               "what": "per step: tws_upload(WATER) from pinned host memory, tws_step(1), tws_readback(WATER) + tws_readback(VELOCITY) into pinned host memory; "
+                       "terrain and flux stay device-resident as in the reference (its state never leaves the GPU)"}
+
+    # ---- strips vs whole grid (tests) ------------------------------------------------------------------
+    if args.verify_strips and world > 1:
+        n_chk = 12
+        barrier()                                    # strips must be quiescent around a reset
+        sim.CreateHeightmapFromNoiseAndResetSim()
+        barrier()
+        sim.inject_brush(W / 2 + 0.25, plan.rows(1)[0] - 0.5, 5.0, 64.0)
+        sim.step(n_chk)
+        sim.sync()
+        mine = (sim.readback(tws.FIELD_WATER), sim.readback(tws.FIELD_FLUX), sim.readback(tws.FIELD_VELOCITY).view(np.uint16))
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(mine, parts, dst=0)
+        if rank == 0:
+            with tws.Terrain(W, height=Hg, backend=tws.BACKEND_UNFUSED, device=local) as whole:
+                whole.CreateHeightmapFromNoiseAndResetSim()
+                whole.inject_brush(W / 2 + 0.25, plan.rows(1)[0] - 0.5, 5.0, 64.0)
+                whole.step(n_chk)
+                ok = (np.array_equal(np.concatenate([p[0] for p in parts]).view(np.uint32), whole.readback(tws.FIELD_WATER).view(np.uint32))
+                      and np.array_equal(np.concatenate([p[1] for p in parts]).view(np.uint32), whole.readback(tws.FIELD_FLUX).view(np.uint32))
+                      and np.array_equal(np.concatenate([p[2] for p in parts]), whole.readback(tws.FIELD_VELOCITY).view(np.uint16)))
+            print("STRIPS_VERIFIED" if ok else "STRIPS_MISMATCH", flush=True)
+            if not ok:
+                raise SystemExit(3)
+        dist.barrier()
+
+    sim.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, cores, sample, _ = cpu_oracle_throughput(W, 4, 1, budget_s=20.0)
+        cpu = {"value": val, "unit": "Gcell-updates/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": "Gcell-updates/s per sim step (fp32)", "value": value, "unit": "Gcell-updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "roofline": roofline,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "per_gpu_value": value / world,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -114,11 +114,13 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    import os
+    path = Path(os.environ.get("TWS_LIB", str(LIB_PATH)))      # TWS_LIB: tuning builds of the same CUDA library
+    if not path.exists():
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(terrainwatersim_b200 has no CPU or pure-Python path)")
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(path))
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -40,6 +40,23 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
+def build_variant(out: Path, defines, verbose: bool = False) -> Path:
+    """Tuning helper: build a copy of the library with extra -D defines (not used by the product)."""
+    host_cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else None
+    cmd = [find_nvcc(), *NVCC_FLAGS] + [f"-D{d}" for d in defines]
+    if host_cxx:
+        cmd += ["-ccbin", host_cxx]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", str(out), *[str(CSRC / s) for s in SOURCES]]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout + res.stderr)
+    return out
+
+
 def build_libtws(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB_PATH

@@ -28,21 +28,48 @@ namespace tws {
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ float max0(float v) { return (v > 0.0f) ? v : 0.0f; }   // flowUpdate.comp:54
 
-// flowUpdate.comp:44-59.  f* in: old outflow, out: new outflow.
-__device__ __forceinline__ void flux_cell(float Hc, float Hxp, float Hxm, float Hyp, float Hym, float depth,
+// flowUpdate.comp:44-57 for one cell.  f* in: old outflow, out: clamped-at-zero new outflow
+// BEFORE the "cannot drain below zero" scaling; returns total = (sum f') * areaInv (:57).
+__device__ __forceinline__ float flux_raw(float Hc, float Hxp, float Hxm, float Hyp, float Hym,
                                           float& fx, float& fy, float& fz, float& fw, const StepConsts& c) {
   float nx = Hc - Hxp, ny = Hc - Hxm, nz = Hc - Hyp, nw = Hc - Hym;                  // :44-47
   nx = __fadd_rn(__fmul_rn(fx, c.friction), __fmul_rn(nx, c.accel));                 // :53
   ny = __fadd_rn(__fmul_rn(fy, c.friction), __fmul_rn(ny, c.accel));
   nz = __fadd_rn(__fmul_rn(fz, c.friction), __fmul_rn(nz, c.accel));
   nw = __fadd_rn(__fmul_rn(fw, c.friction), __fmul_rn(nw, c.accel));
-  nx = max0(nx); ny = max0(ny); nz = max0(nz); nw = max0(nw);                        // :54
-  const float total = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(nx, ny), nz), nw), c.area_inv);   // :57
-  if (total > depth) {                                                               // :58
-    const float s = __fdiv_rn(depth, total);                                         // :59
-    nx = __fmul_rn(nx, s); ny = __fmul_rn(ny, s); nz = __fmul_rn(nz, s); nw = __fmul_rn(nw, s);
+  fx = max0(nx); fy = max0(ny); fz = max0(nz); fw = max0(nw);                        // :54
+  return __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(fx, fy), fz), fw), c.area_inv);     // :57
+}
+
+// flowUpdate.comp:58-59 for the four cells of one float4 group: if (total > a) f' *= a / total.
+// The IEEE division is needed only for a wet cell that would drain completely this step —
+// rare — so the common path is branch free: scale = 1 when total <= a (x*1 == x bit for bit,
+// the shader does not multiply at all there), scale = 0 when a == 0 (0/total == +0 for every
+// total > 0), and ONE warp-level branch covers the cells that really divide.
+__device__ __forceinline__ void flux_scale4(const float (&total)[4], const float (&depth)[4], float (&s)[4]) {
+  bool need = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool over = total[i] > depth[i];
+    const bool dry = depth[i] == 0.0f;
+    s[i] = over ? 0.0f : 1.0f;
+    need = need || (over && !dry);
   }
-  fx = nx; fy = ny; fz = nz; fw = nw;
+  if (need) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (total[i] > depth[i] && depth[i] != 0.0f) s[i] = __fdiv_rn(depth[i], total[i]);
+  }
+}
+
+// Scalar form used by the unfused baseline.
+__device__ __forceinline__ void flux_cell(float Hc, float Hxp, float Hxm, float Hyp, float Hym, float depth,
+                                          float& fx, float& fy, float& fz, float& fw, const StepConsts& c) {
+  const float total = flux_raw(Hc, Hxp, Hxm, Hyp, Hym, fx, fy, fz, fw, c);
+  if (total > depth) {                                                               // :58
+    const float s = (depth == 0.0f) ? 0.0f : __fdiv_rn(depth, total);                // :59
+    fx = __fmul_rn(fx, s); fy = __fmul_rn(fy, s); fz = __fmul_rn(fz, s); fw = __fmul_rn(fw, s);
+  }
 }
 
 // flowApply.comp:38-46.  Returns the new depth; vx, vy the flow vector.
@@ -172,164 +199,257 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int K, int OX_, int OY_, int NT_>
+// Tile configuration of the pipelined kernel.  One persistent CTA per SM owns TWO staging
+// buffers: while the passes run on tile j in one buffer the TMA unit fills the other with
+// tile j+1, so the SM never idles on the load and HBM never idles on the compute.
+template <int K_, int OX_, int OY_, int NT_>
 struct FusedCfg {
-  static constexpr int OX = OX_, OY = OY_, NT = NT_;
+  static constexpr int K = K_, OX = OX_, OY = OY_, NT = NT_;
   static constexpr int HX = ((2 * K + 3) / 4) * 4;   // x halo rounded to whole float4 groups
   static constexpr int HY = 2 * K;
   static constexpr int SX = OX + 2 * HX, SY = OY + 2 * HY;
+  static constexpr int NG = SX / 4;                  // float4 groups per staged row
   static constexpr int PLANE = SX * SY;              // floats per staged plane
-  static constexpr size_t SMEM = (size_t)6 * PLANE * sizeof(float);
+  static constexpr int STAGE = 6 * PLANE;            // h, d, F x4
+  static constexpr int STAGES = 2;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE * sizeof(float);
   static_assert(OX % 4 == 0 && SX <= 256 && SY <= 256, "TMA box limits");
   static_assert((PLANE * 4) % 128 == 0, "staged planes must keep 128 B alignment");
+  static_assert(NT % 32 == 0, "whole warps");
 };
 
 struct FusedOut {          // plane pointers at local row 0
   float* d; float* F[4]; uint32_t* v;
 };
 
-template <class C, int K>
-__global__ void __launch_bounds__(C::NT) fused_step_kernel(const __grid_constant__ CUtensorMap tm_h,
-                                                           const __grid_constant__ CUtensorMap tm_d,
-                                                           const __grid_constant__ CUtensorMap tm_f0,
-                                                           const __grid_constant__ CUtensorMap tm_f1,
-                                                           const __grid_constant__ CUtensorMap tm_f2,
-                                                           const __grid_constant__ CUtensorMap tm_f3,
-                                                           FusedOut out, Geom g, StepConsts c, int ty0, int tma_y_bias) {
-  constexpr int OX = C::OX, OY = C::OY, NT = C::NT, HX = C::HX, HY = C::HY, SX = C::SX, PLANE = C::PLANE;
+struct TileCtx {
+  int sx0;        // grid x of staged column 0
+  int ly0;        // LOCAL row of staged row 0
+  int gy0;        // GLOBAL row of staged row 0
+};
+
+// One flux pass (flowUpdate.comp) over staged rows [HY-M, HY+OY+M), full staged width.
+// Full-width rows make the float4 items of a pass contiguous in shared memory, so a warp's
+// LDS.128 are conflict free and the x-neighbour values of lanes 1..30 come from warp
+// shuffles; only lanes 0 and 31 read the neighbouring cell from shared memory.
+template <class C, bool EDGE, bool LAST>
+__device__ __forceinline__ void flux_pass(float* __restrict__ st, const int M, const TileCtx& tc, const FusedOut& out, const Geom& g,
+                                          const StepConsts& c, const int tid) {
+  constexpr int NG = C::NG, SX = C::SX, PLANE = C::PLANE, NT = C::NT;
+  float* sh = st; float* sd = st + PLANE;
+  float* sFxp = st + 2 * PLANE; float* sFxm = st + 3 * PLANE; float* sFyp = st + 4 * PLANE; float* sFym = st + 5 * PLANE;
+  const int R0 = C::HY - M;
+  const int nitems = NG * (C::OY + 2 * M);
+  const int lane = tid & 31;
+  for (int base = tid - lane; base < nitems; base += NT) {
+    const int it = base + lane;
+    const bool active = it < nitems;
+    const int itc = active ? it : nitems - 1;
+    const int o = (R0 * NG + itc) * 4;
+    const float4 dC = ld4(sd + o);
+    const float4 HC = add4(dC, ld4(sh + o));
+    const float4 HU = add4(ld4(sd + o - SX), ld4(sh + o - SX));
+    const float4 HD = add4(ld4(sd + o + SX), ld4(sh + o + SX));
+    float HL = __shfl_up_sync(0xffffffffu, HC.w, 1);
+    float HR = __shfl_down_sync(0xffffffffu, HC.x, 1);
+    if (lane == 0) HL = sd[o - 1] + sh[o - 1];
+    if (lane == 31) HR = sd[o + 4] + sh[o + 4];
+    float4 fx = ld4(sFxp + o), fy = ld4(sFxm + o), fz = ld4(sFyp + o), fw = ld4(sFym + o);
+    float* pfx = &fx.x; float* pfy = &fy.x; float* pfz = &fz.x; float* pfw = &fw.x;
+    const int rr = itc / NG, gg = itc - rr * NG;
+    const int r = R0 + rr, x = gg * 4;
+    const int gy = tc.gy0 + r, gx0 = tc.sx0 + x;
+    const bool row_in = (unsigned)gy < (unsigned)g.Hg;
+    float total[4], scale[4];
+    const float dep[4] = {dC.x, dC.y, dC.z, dC.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float Hc = comp(HC, i);
+      float hxp = (i < 3) ? comp(HC, i + 1) : HR;
+      float hxm = (i > 0) ? comp(HC, i - 1) : HL;
+      float hyp = comp(HD, i), hym = comp(HU, i);
+      if (EDGE && c.closed) {
+        const int gx = gx0 + i;
+        if (gx + 1 >= g.W) hxp = Hc;
+        if (gx - 1 < 0) hxm = Hc;
+        if (gy + 1 >= g.Hg) hyp = Hc;
+        if (gy - 1 < 0) hym = Hc;
+      }
+      total[i] = flux_raw(Hc, hxp, hxm, hyp, hym, pfx[i], pfy[i], pfz[i], pfw[i], c);
+    }
+    flux_scale4(total, dep, scale);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pfx[i] = __fmul_rn(pfx[i], scale[i]); pfy[i] = __fmul_rn(pfy[i], scale[i]);
+      pfz[i] = __fmul_rn(pfz[i], scale[i]); pfw[i] = __fmul_rn(pfw[i], scale[i]);
+      if (EDGE && !(row_in && (unsigned)(gx0 + i) < (unsigned)g.W)) { pfx[i] = 0.f; pfy[i] = 0.f; pfz[i] = 0.f; pfw[i] = 0.f; }
+    }
+    if (active) {
+      st4(sFxp + o, fx); st4(sFxm + o, fy); st4(sFyp + o, fz); st4(sFym + o, fw);
+      if (LAST) {
+        const int lr = tc.ly0 + r;                     // local row
+        bool store = x >= C::HX && x < C::HX + C::OX && r >= C::HY && r < C::HY + C::OY;
+        if (EDGE) store = store && lr < g.rows && gx0 < g.pitch;
+        if (store) {
+          const size_t go = (size_t)((long long)lr * g.pitch) + gx0;
+          st4(out.F[0] + go, fx); st4(out.F[1] + go, fy); st4(out.F[2] + go, fz); st4(out.F[3] + go, fw);
+        }
+      }
+    }
+  }
+}
+
+// One depth pass (flowApply.comp).  Non-last levels: rows [HY-M, HY+OY+M), full width, depth
+// written back in place.  Last level (M = 0): exactly the output tile, depth and the fp16
+// flow vector go straight to HBM.
+template <class C, bool EDGE, bool LAST>
+__device__ __forceinline__ void depth_pass(float* __restrict__ st, const int M, const TileCtx& tc, const FusedOut& out, const Geom& g,
+                                           const StepConsts& c, const int tid) {
+  constexpr int SX = C::SX, PLANE = C::PLANE, NT = C::NT;
+  constexpr int NG = LAST ? C::OX / 4 : C::NG;
+  float* sd = st + PLANE;
+  const float* sFxp = st + 2 * PLANE; const float* sFxm = st + 3 * PLANE; const float* sFyp = st + 4 * PLANE; const float* sFym = st + 5 * PLANE;
+  const int R0 = C::HY - M;
+  const int nitems = NG * (C::OY + 2 * M);
+  const int lane = tid & 31;
+  for (int base = tid - lane; base < nitems; base += NT) {
+    const int it = base + lane;
+    const bool active = it < nitems;
+    const int itc = active ? it : nitems - 1;
+    const int rr = itc / NG, gg = itc - rr * NG;
+    const int r = R0 + rr, x = LAST ? C::HX + gg * 4 : gg * 4;
+    const int o = r * SX + x;
+    const float4 fx = ld4(sFxp + o), fy = ld4(sFxm + o), fz = ld4(sFyp + o), fw = ld4(sFym + o);
+    const float4 iy1 = ld4(sFym + o + SX);         // F(x,y+1).w
+    const float4 iy0 = ld4(sFyp + o - SX);         // F(x,y-1).z
+    float l = __shfl_up_sync(0xffffffffu, fx.w, 1);      // F(x-1,y).x
+    float rgt = __shfl_down_sync(0xffffffffu, fy.x, 1);  // F(x+1,y).y
+    if (lane == 0 || (LAST && gg == 0)) l = sFxp[o - 1];
+    if (lane == 31 || (LAST && gg == NG - 1)) rgt = sFxm[o + 4];
+    const float4 dC = ld4(sd + o);
+    const int gy = tc.gy0 + r, gx0 = tc.sx0 + x;
+    const bool row_in = (unsigned)gy < (unsigned)g.Hg;
+    float nd[4]; uint32_t nv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float iX1 = (i < 3) ? comp(fy, i + 1) : rgt;
+      const float iX0 = (i > 0) ? comp(fx, i - 1) : l;
+      float vx, vy;
+      nd[i] = apply_cell(comp(dC, i), comp(fx, i), comp(fy, i), comp(fz, i), comp(fw, i), iX1, iX0, comp(iy1, i), comp(iy0, i), c, vx, vy);
+      if (LAST) nv[i] = pack_half2(vx, vy);
+      if (EDGE && !(row_in && (unsigned)(gx0 + i) < (unsigned)g.W)) { nd[i] = 0.f; if (LAST) nv[i] = 0u; }
+    }
+    if (active) {
+      if (!LAST) {
+        st4(sd + o, make_float4(nd[0], nd[1], nd[2], nd[3]));
+      } else {
+        const int lr = tc.ly0 + r;
+        if (!EDGE || (lr < g.rows && gx0 < g.pitch)) {
+          const size_t go = (size_t)((long long)lr * g.pitch) + gx0;
+          st4(out.d + go, make_float4(nd[0], nd[1], nd[2], nd[3]));
+          *reinterpret_cast<uint4*>(out.v + go) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+        }
+      }
+    }
+  }
+}
+
+template <class C, bool EDGE>
+__device__ __forceinline__ void run_tile(float* st, const TileCtx& tc, const FusedOut& out, const Geom& g, const StepConsts& c, const int tid) {
+  constexpr int K = C::K;
+#pragma unroll 1
+  for (int t = 1; t < K; ++t) {
+    flux_pass<C, EDGE, false>(st, 2 * (K - t) + 1, tc, out, g, c, tid);
+    __syncthreads();
+    depth_pass<C, EDGE, false>(st, 2 * (K - t), tc, out, g, c, tid);
+    __syncthreads();
+  }
+  flux_pass<C, EDGE, true>(st, 1, tc, out, g, c, tid);
+  __syncthreads();
+  depth_pass<C, EDGE, true>(st, 0, tc, out, g, c, tid);
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, 1) fused_step_kernel(const __grid_constant__ CUtensorMap tm_h,
+                                                              const __grid_constant__ CUtensorMap tm_d,
+                                                              const __grid_constant__ CUtensorMap tm_f0,
+                                                              const __grid_constant__ CUtensorMap tm_f1,
+                                                              const __grid_constant__ CUtensorMap tm_f2,
+                                                              const __grid_constant__ CUtensorMap tm_f3,
+                                                              FusedOut out, Geom g, StepConsts c, int ty0, int tiles_x, int n_tiles,
+                                                              int tma_y_bias) {
+  constexpr int OX = C::OX, OY = C::OY, HX = C::HX, HY = C::HY, SX = C::SX, SY = C::SY, PLANE = C::PLANE, STAGE = C::STAGE;
   extern __shared__ __align__(1024) float smem[];
-  __shared__ uint64_t bar;
-  float* sh = smem;
-  float* sd = smem + PLANE;
-  float* sFxp = smem + 2 * PLANE;
-  float* sFxm = smem + 3 * PLANE;
-  float* sFyp = smem + 4 * PLANE;
-  float* sFym = smem + 5 * PLANE;
-
+  __shared__ uint64_t full[2];
   const int tid = threadIdx.x;
-  const int ox0 = blockIdx.x * OX;                   // first output column
-  const int oy0 = (ty0 + blockIdx.y) * OY;           // first output LOCAL row
-  const int sx0 = ox0 - HX, sy0 = oy0 - HY;          // staged origin (grid x, local row)
 
+  auto tile_ctx = [&](int tile) {
+    const int by = tile / tiles_x, bx = tile - by * tiles_x;
+    TileCtx tc;
+    tc.sx0 = bx * OX - HX;
+    tc.ly0 = (ty0 + by) * OY - HY;
+    tc.gy0 = g.row0 + tc.ly0;
+    return tc;
+  };
+  auto issue = [&](int tile, int stage) {          // one thread
+    const TileCtx tc = tile_ctx(tile);
+    float* st = smem + stage * STAGE;
+    mbar_expect_tx(&full[stage], (uint32_t)(STAGE * sizeof(float)));
+    const int ty = tc.ly0 + tma_y_bias;
+    tma_load_2d(st, &tm_h, tc.sx0, ty, &full[stage]);
+    tma_load_2d(st + PLANE, &tm_d, tc.sx0, ty, &full[stage]);
+    tma_load_2d(st + 2 * PLANE, &tm_f0, tc.sx0, ty, &full[stage]);
+    tma_load_2d(st + 3 * PLANE, &tm_f1, tc.sx0, ty, &full[stage]);
+    tma_load_2d(st + 4 * PLANE, &tm_f2, tc.sx0, ty, &full[stage]);
+    tma_load_2d(st + 5 * PLANE, &tm_f3, tc.sx0, ty, &full[stage]);
+  };
+
+  const int first = blockIdx.x, stride = gridDim.x;
   if (tid == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (first < n_tiles) issue(first, 0);
+    if (first + stride < n_tiles) issue(first + stride, 1);
   }
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&bar, (uint32_t)C::SMEM);
-    const int ty = sy0 + tma_y_bias;
-    tma_load_2d(sh, &tm_h, sx0, ty, &bar);
-    tma_load_2d(sd, &tm_d, sx0, ty, &bar);
-    tma_load_2d(sFxp, &tm_f0, sx0, ty, &bar);
-    tma_load_2d(sFxm, &tm_f1, sx0, ty, &bar);
-    tma_load_2d(sFyp, &tm_f2, sx0, ty, &bar);
-    tma_load_2d(sFym, &tm_f3, sx0, ty, &bar);
-  }
-  mbar_wait(&bar, 0);
 
-  const int gy_base = g.row0 + sy0;                  // global row of staged row 0
-
-#pragma unroll
-  for (int t = 1; t <= K; ++t) {
-    // ---------------- flux pass of level t: margin 2(K-t)+1 around the output tile ----
-    {
-      const int M = 2 * (K - t) + 1;
-      const int X0 = (HX - M) / 4, X1 = (HX + OX + M + 3) / 4, NG = X1 - X0;
-      const int R0 = HY - M, NR = OY + 2 * M;
-      const bool last = (t == K);
-      for (int it = tid; it < NG * NR; it += NT) {
-        const int rr = it / NG, gg = it - rr * NG;
-        const int r = R0 + rr, x = (X0 + gg) * 4;
-        const int o = r * SX + x;
-        const int gy = gy_base + r, gx0 = sx0 + x;
-        const float4 dC = ld4(sd + o);
-        const float4 HC = add4(dC, ld4(sh + o));
-        const float4 HU = add4(ld4(sd + o - SX), ld4(sh + o - SX));
-        const float4 HD = add4(ld4(sd + o + SX), ld4(sh + o + SX));
-        const float HL = sd[o - 1] + sh[o - 1];
-        const float HR = sd[o + 4] + sh[o + 4];
-        float4 fx = ld4(sFxp + o), fy = ld4(sFxm + o), fz = ld4(sFyp + o), fw = ld4(sFym + o);
-        float* pfx = &fx.x; float* pfy = &fy.x; float* pfz = &fz.x; float* pfw = &fw.x;
-        const bool row_in = (unsigned)gy < (unsigned)g.Hg;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int gx = gx0 + i;
-          const float Hc = comp(HC, i);
-          float hxp = (i < 3) ? comp(HC, i + 1) : HR;
-          float hxm = (i > 0) ? comp(HC, i - 1) : HL;
-          float hyp = comp(HD, i), hym = comp(HU, i);
-          if (c.closed) {
-            if (gx + 1 >= g.W) hxp = Hc;
-            if (gx - 1 < 0) hxm = Hc;
-            if (gy + 1 >= g.Hg) hyp = Hc;
-            if (gy - 1 < 0) hym = Hc;
-          }
-          flux_cell(Hc, hxp, hxm, hyp, hym, comp(dC, i), pfx[i], pfy[i], pfz[i], pfw[i], c);
-          if (!(row_in && (unsigned)gx < (unsigned)g.W)) { pfx[i] = 0.f; pfy[i] = 0.f; pfz[i] = 0.f; pfw[i] = 0.f; }
-        }
-        st4(sFxp + o, fx); st4(sFxm + o, fy); st4(sFyp + o, fz); st4(sFym + o, fw);
-        if (last) {
-          const int lr = sy0 + r;                      // local row
-          if (x >= HX && x < HX + OX && r >= HY && r < HY + OY && lr < g.rows && gx0 < g.pitch) {
-            const size_t go = (size_t)((long long)lr * g.pitch) + gx0;
-            st4(out.F[0] + go, fx); st4(out.F[1] + go, fy); st4(out.F[2] + go, fz); st4(out.F[3] + go, fw);
-          }
-        }
-      }
+  int j = 0;
+  for (int tile = first; tile < n_tiles; tile += stride, ++j) {
+    const int stage = j & 1;
+    float* st = smem + stage * STAGE;
+    const TileCtx tc = tile_ctx(tile);
+    mbar_wait(&full[stage], (uint32_t)((j >> 1) & 1));
+    // Tiles whose staged window lies fully inside the grid and whose outputs are all owned rows
+    // need no exterior masks, no boundary-mode handling and no store guards.
+    const bool edge = tc.sx0 < 0 || tc.sx0 + SX > g.W || tc.gy0 < 0 || tc.gy0 + SY > g.Hg || tc.ly0 + HY + OY > g.rows;
+    if (edge) run_tile<C, true>(st, tc, out, g, c, tid);
+    else run_tile<C, false>(st, tc, out, g, c, tid);
+    __syncthreads();                                  // every read of this stage is done
+    if (tid == 0 && tile + 2 * stride < n_tiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(tile + 2 * stride, stage);
     }
-    __syncthreads();
-    // ---------------- depth pass of level t: margin 2(K-t) ------------------------------
-    {
-      const int M = 2 * (K - t);
-      const int X0 = (HX - M) / 4, X1 = (HX + OX + M + 3) / 4, NG = X1 - X0;
-      const int R0 = HY - M, NR = OY + 2 * M;
-      const bool last = (t == K);
-      for (int it = tid; it < NG * NR; it += NT) {
-        const int rr = it / NG, gg = it - rr * NG;
-        const int r = R0 + rr, x = (X0 + gg) * 4;
-        const int o = r * SX + x;
-        const int gy = gy_base + r, gx0 = sx0 + x;
-        const float4 fx = ld4(sFxp + o), fy = ld4(sFxm + o), fz = ld4(sFyp + o), fw = ld4(sFym + o);
-        const float4 iy1 = ld4(sFym + o + SX);         // F(x,y+1).w
-        const float4 iy0 = ld4(sFyp + o - SX);         // F(x,y-1).z
-        const float l = sFxp[o - 1];                   // F(x-1,y).x
-        const float rgt = sFxm[o + 4];                 // F(x+1,y).y
-        const float4 dC = ld4(sd + o);
-        const bool row_in = (unsigned)gy < (unsigned)g.Hg;
-        float nd[4]; uint32_t nv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float iX1 = (i < 3) ? comp(fy, i + 1) : rgt;
-          const float iX0 = (i > 0) ? comp(fx, i - 1) : l;
-          float vx, vy;
-          nd[i] = apply_cell(comp(dC, i), comp(fx, i), comp(fy, i), comp(fz, i), comp(fw, i), iX1, iX0, comp(iy1, i),
-                             comp(iy0, i), c, vx, vy);
-          nv[i] = pack_half2(vx, vy);
-          if (!(row_in && (unsigned)(gx0 + i) < (unsigned)g.W)) { nd[i] = 0.f; nv[i] = 0u; }
-        }
-        if (!last) {
-          st4(sd + o, make_float4(nd[0], nd[1], nd[2], nd[3]));
-        } else {
-          const int lr = sy0 + r;
-          if (lr < g.rows && gx0 < g.pitch) {
-            const size_t go = (size_t)((long long)lr * g.pitch) + gx0;
-            st4(out.d + go, make_float4(nd[0], nd[1], nd[2], nd[3]));
-            *reinterpret_cast<uint4*>(out.v + go) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
-          }
-        }
-      }
-    }
-    if (t < K) __syncthreads();
   }
 }
 
 // ---- per-K tile configuration ---------------------------------------------------------
 template <int K> struct CfgFor;
-template <> struct CfgFor<1> { using type = FusedCfg<1, 128, 28, 256>; };
-template <> struct CfgFor<2> { using type = FusedCfg<2, 128, 24, 256>; };
-template <> struct CfgFor<3> { using type = FusedCfg<3, 112, 52, 512>; };
-template <> struct CfgFor<4> { using type = FusedCfg<4, 112, 48, 512>; };
+#ifndef TWS_FUSED_NT
+#define TWS_FUSED_NT 512
+#endif
+template <> struct CfgFor<1> { using type = FusedCfg<1, 128, 28, TWS_FUSED_NT>; };
+template <> struct CfgFor<2> { using type = FusedCfg<2, 128, 24, TWS_FUSED_NT>; };
+template <> struct CfgFor<3> { using type = FusedCfg<3, 120, 20, TWS_FUSED_NT>; };
+template <> struct CfgFor<4> { using type = FusedCfg<4, 120, 16, TWS_FUSED_NT>; };
+
+static int sm_count_of_current_device() {
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!cached[dev & 63]) cudaDeviceGetAttribute(&cached[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+  return cached[dev & 63] > 0 ? cached[dev & 63] : 148;
+}
 
 template <int K>
 static cudaError_t launch_fused_k(const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int ty0,
@@ -338,22 +458,26 @@ static cudaError_t launch_fused_k(const Geom& g, const Planes& p, const TmaSet& 
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = fused_step_kernel<C, K>;
+  auto kern = fused_step_kernel<C>;
   if (!attr_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
+  if (ty1 <= ty0) return cudaSuccess;
   const int dst = 1 - src;
   const size_t row0_off = (size_t)TWS_HALO_ROWS * g.pitch;
   FusedOut out;
   out.d = p.d[dst] + row0_off;
   for (int i = 0; i < 4; ++i) out.F[i] = p.F[dst][i] + row0_off;
   out.v = p.v + row0_off;
-  dim3 grid((g.W + C::OX - 1) / C::OX, ty1 - ty0, 1);
-  if (grid.y == 0) return cudaSuccess;
+  const int tiles_x = (g.W + C::OX - 1) / C::OX;
+  const long long n_tiles = (long long)tiles_x * (ty1 - ty0);
+  if (n_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+  const int sms = sm_count_of_current_device();
+  const int grid = (int)(n_tiles < sms ? n_tiles : sms);     // one persistent CTA per SM
   const int bias = g.has_up ? TWS_HALO_ROWS : 0;
-  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], tma.m[2], tma.m[3], tma.m[4], tma.m[5], out, g, c, ty0, bias);
+  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], tma.m[2], tma.m[3], tma.m[4], tma.m[5], out, g, c, ty0, tiles_x, (int)n_tiles, bias);
   return cudaGetLastError();
 }
 

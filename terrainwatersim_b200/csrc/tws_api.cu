@@ -500,7 +500,14 @@ tws_status tws_inject_brush(tws_sim* s, float cx, float cy, float intensity, flo
   if (bad_float(size_sq) || !(size_sq > 0.0f)) return fail(s, TWS_ERR_INVALID, "brush size_sq must be > 0");
   DeviceGuard guard(s->prm.device);
   const bool strip = s->geom.has_up || s->geom.has_down;
-  if (strip) TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));
+  if (strip) {
+    // The brush also edits this strip's copy of the neighbours' edge rows (halo rows), so the
+    // neighbours' pushes of the last block must have landed first: wait for their flags.
+    if (!s->connected) return fail(s, TWS_ERR_STATE, "strip sim used before tws_halo_connect");
+    TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));
+    TWS_CUDA(s, launch_wait_flags(s->ctrl, s->geom.has_up, s->geom.has_down, s->epoch, s->st_main));
+    s->launches += 1;
+  }
   int launched = 0;
   TWS_CUDA(s, launch_brush(s->geom, s->planes.d[s->cur] + (size_t)TWS_HALO_ROWS * s->geom.pitch, cx, cy, intensity, size_sq, s->st_main, &launched));
   s->launches += launched;
