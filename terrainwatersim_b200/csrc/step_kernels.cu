@@ -228,40 +228,45 @@ struct TileCtx {
   int gy0;        // GLOBAL row of staged row 0
 };
 
-// One flux pass (flowUpdate.comp) over staged rows [HY-M, HY+OY+M), full staged width.
-// Full-width rows make the float4 items of a pass contiguous in shared memory, so a warp's
-// LDS.128 are conflict free and the x-neighbour values of lanes 1..30 come from warp
-// shuffles; only lanes 0 and 31 read the neighbouring cell from shared memory.
-template <class C, bool EDGE, bool LAST>
-__device__ __forceinline__ void flux_pass(float* __restrict__ st, const int M, const TileCtx& tc, const FusedOut& out, const Geom& g,
-                                          const StepConsts& c, const int tid) {
-  constexpr int NG = C::NG, SX = C::SX, PLANE = C::PLANE, NT = C::NT;
-  float* sh = st; float* sd = st + PLANE;
+// ---- register-resident tile update ---------------------------------------------------------
+// Every thread OWNS up to IPT float4 groups ("items") of the staged tile (rows 1..SY-2, full
+// staged width) for the whole tile: their terrain, depth and four flux values are pulled out
+// of the TMA landing buffers into registers once and stay there across all K levels.  Only
+// what a NEIGHBOUR needs goes through shared memory:
+//   sH   (reuses the depth landing plane)  water level d+h, read by the rows above/below;
+//   sFyp / sFym (their landing planes)     +Y / -Y outflow, read by the rows below/above;
+//   x-neighbours sit in the adjacent lane (items are contiguous along x, full-width rows are
+//   contiguous in memory) and are exchanged with warp shuffles; lanes 0 / 31 fall back to one
+//   scalar shared-memory slot written by the neighbouring warp's edge lane.
+// Per level and item that is 4 LDS.128 + 3 STS.128 instead of 17 + 5, and the flux never
+// round-trips through shared memory for its owner.
+// Passes run over all owned rows at every level: cells outside the shrinking valid region
+// hold garbage that by construction never reaches the OX x OY output centre.
+template <class C, bool EDGE, bool LAST, int IPT>
+__device__ __forceinline__ void flux_level(float* __restrict__ st, const int (&o)[IPT], const bool (&valid)[IPT], const float4 (&h)[IPT],
+                                           const float4 (&d)[IPT], float4 (&fx)[IPT], float4 (&fy)[IPT], float4 (&fz)[IPT], float4 (&fw)[IPT],
+                                           const TileCtx& tc, const FusedOut& out, const Geom& g, const StepConsts& c, const int lane,
+                                           const int M) {
+  constexpr int SX = C::SX, PLANE = C::PLANE;
+  const float* sH = st + PLANE;
   float* sFxp = st + 2 * PLANE; float* sFxm = st + 3 * PLANE; float* sFyp = st + 4 * PLANE; float* sFym = st + 5 * PLANE;
-  const int R0 = C::HY - M;
-  const int nitems = NG * (C::OY + 2 * M);
-  const int lane = tid & 31;
-  for (int base = tid - lane; base < nitems; base += NT) {
-    const int it = base + lane;
-    const bool active = it < nitems;
-    const int itc = active ? it : nitems - 1;
-    const int o = (R0 * NG + itc) * 4;
-    const float4 dC = ld4(sd + o);
-    const float4 HC = add4(dC, ld4(sh + o));
-    const float4 HU = add4(ld4(sd + o - SX), ld4(sh + o - SX));
-    const float4 HD = add4(ld4(sd + o + SX), ld4(sh + o + SX));
+#pragma unroll
+  for (int q = 0; q < IPT; ++q) {
+    const int oq = o[q];
+    const float4 HC = add4(d[q], h[q]);                                              // a + r, flowUpdate.comp:34
+    const float4 HU = ld4(sH + oq - SX), HD = ld4(sH + oq + SX);
     float HL = __shfl_up_sync(0xffffffffu, HC.w, 1);
     float HR = __shfl_down_sync(0xffffffffu, HC.x, 1);
-    if (lane == 0) HL = sd[o - 1] + sh[o - 1];
-    if (lane == 31) HR = sd[o + 4] + sh[o + 4];
-    float4 fx = ld4(sFxp + o), fy = ld4(sFxm + o), fz = ld4(sFyp + o), fw = ld4(sFym + o);
-    float* pfx = &fx.x; float* pfy = &fy.x; float* pfz = &fz.x; float* pfw = &fw.x;
-    const int rr = itc / NG, gg = itc - rr * NG;
-    const int r = R0 + rr, x = gg * 4;
+    if (lane == 0) HL = sH[oq - 1];
+    if (lane == 31) HR = sH[oq + 4];
+    float* pfx = &fx[q].x; float* pfy = &fy[q].x; float* pfz = &fz[q].x; float* pfw = &fw[q].x;
+    const int r = oq / SX, x = oq - r * SX;
+    // rows outside this level's margin M around the output tile feed nothing that is kept
+    if (!valid[q] || r < C::HY - M || r >= C::HY + C::OY + M) continue;
     const int gy = tc.gy0 + r, gx0 = tc.sx0 + x;
     const bool row_in = (unsigned)gy < (unsigned)g.Hg;
     float total[4], scale[4];
-    const float dep[4] = {dC.x, dC.y, dC.z, dC.w};
+    const float dep[4] = {d[q].x, d[q].y, d[q].z, d[q].w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float Hc = comp(HC, i);
@@ -284,89 +289,112 @@ __device__ __forceinline__ void flux_pass(float* __restrict__ st, const int M, c
       pfz[i] = __fmul_rn(pfz[i], scale[i]); pfw[i] = __fmul_rn(pfw[i], scale[i]);
       if (EDGE && !(row_in && (unsigned)(gx0 + i) < (unsigned)g.W)) { pfx[i] = 0.f; pfy[i] = 0.f; pfz[i] = 0.f; pfw[i] = 0.f; }
     }
-    if (active) {
-      st4(sFxp + o, fx); st4(sFxm + o, fy); st4(sFyp + o, fz); st4(sFym + o, fw);
+    {
+      st4(sFyp + oq, fz[q]); st4(sFym + oq, fw[q]);
+      if (lane == 31) sFxp[oq + 3] = fx[q].w;          // for lane 0 of the next warp
+      if (lane == 0) sFxm[oq] = fy[q].x;               // for lane 31 of the previous warp
       if (LAST) {
         const int lr = tc.ly0 + r;                     // local row
         bool store = x >= C::HX && x < C::HX + C::OX && r >= C::HY && r < C::HY + C::OY;
         if (EDGE) store = store && lr < g.rows && gx0 < g.pitch;
         if (store) {
           const size_t go = (size_t)((long long)lr * g.pitch) + gx0;
-          st4(out.F[0] + go, fx); st4(out.F[1] + go, fy); st4(out.F[2] + go, fz); st4(out.F[3] + go, fw);
+          st4(out.F[0] + go, fx[q]); st4(out.F[1] + go, fy[q]); st4(out.F[2] + go, fz[q]); st4(out.F[3] + go, fw[q]);
         }
       }
     }
   }
 }
 
-// One depth pass (flowApply.comp).  Non-last levels: rows [HY-M, HY+OY+M), full width, depth
-// written back in place.  Last level (M = 0): exactly the output tile, depth and the fp16
-// flow vector go straight to HBM.
-template <class C, bool EDGE, bool LAST>
-__device__ __forceinline__ void depth_pass(float* __restrict__ st, const int M, const TileCtx& tc, const FusedOut& out, const Geom& g,
-                                           const StepConsts& c, const int tid) {
-  constexpr int SX = C::SX, PLANE = C::PLANE, NT = C::NT;
-  constexpr int NG = LAST ? C::OX / 4 : C::NG;
-  float* sd = st + PLANE;
+template <class C, bool EDGE, bool LAST, int IPT>
+__device__ __forceinline__ void depth_level(float* __restrict__ st, const int (&o)[IPT], const bool (&valid)[IPT], const float4 (&h)[IPT],
+                                            float4 (&d)[IPT], const float4 (&fx)[IPT], const float4 (&fy)[IPT], const float4 (&fz)[IPT],
+                                            const float4 (&fw)[IPT], const TileCtx& tc, const FusedOut& out, const Geom& g,
+                                            const StepConsts& c, const int lane, const int M) {
+  constexpr int SX = C::SX, PLANE = C::PLANE;
+  float* sH = st + PLANE;
   const float* sFxp = st + 2 * PLANE; const float* sFxm = st + 3 * PLANE; const float* sFyp = st + 4 * PLANE; const float* sFym = st + 5 * PLANE;
-  const int R0 = C::HY - M;
-  const int nitems = NG * (C::OY + 2 * M);
-  const int lane = tid & 31;
-  for (int base = tid - lane; base < nitems; base += NT) {
-    const int it = base + lane;
-    const bool active = it < nitems;
-    const int itc = active ? it : nitems - 1;
-    const int rr = itc / NG, gg = itc - rr * NG;
-    const int r = R0 + rr, x = LAST ? C::HX + gg * 4 : gg * 4;
-    const int o = r * SX + x;
-    const float4 fx = ld4(sFxp + o), fy = ld4(sFxm + o), fz = ld4(sFyp + o), fw = ld4(sFym + o);
-    const float4 iy1 = ld4(sFym + o + SX);         // F(x,y+1).w
-    const float4 iy0 = ld4(sFyp + o - SX);         // F(x,y-1).z
-    float l = __shfl_up_sync(0xffffffffu, fx.w, 1);      // F(x-1,y).x
-    float rgt = __shfl_down_sync(0xffffffffu, fy.x, 1);  // F(x+1,y).y
-    if (lane == 0 || (LAST && gg == 0)) l = sFxp[o - 1];
-    if (lane == 31 || (LAST && gg == NG - 1)) rgt = sFxm[o + 4];
-    const float4 dC = ld4(sd + o);
+#pragma unroll
+  for (int q = 0; q < IPT; ++q) {
+    const int oq = o[q];
+    const float4 iy1 = ld4(sFym + oq + SX);            // F(x,y+1).w, flowApply.comp:34
+    const float4 iy0 = ld4(sFyp + oq - SX);            // F(x,y-1).z, :35
+    float l = __shfl_up_sync(0xffffffffu, fx[q].w, 1);       // F(x-1,y).x, :33
+    float rgt = __shfl_down_sync(0xffffffffu, fy[q].x, 1);   // F(x+1,y).y, :32
+    if (lane == 0) l = sFxp[oq - 1];
+    if (lane == 31) rgt = sFxm[oq + 4];
+    const int r = oq / SX, x = oq - r * SX;
     const int gy = tc.gy0 + r, gx0 = tc.sx0 + x;
+    bool store = false;
+    if (LAST) {
+      store = valid[q] && x >= C::HX && x < C::HX + C::OX && r >= C::HY && r < C::HY + C::OY;
+      if (EDGE) store = store && tc.ly0 + r < g.rows && gx0 < g.pitch;
+      if (!store) continue;
+    } else if (!valid[q] || r < C::HY - M || r >= C::HY + C::OY + M) {
+      continue;
+    }
     const bool row_in = (unsigned)gy < (unsigned)g.Hg;
     float nd[4]; uint32_t nv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float iX1 = (i < 3) ? comp(fy, i + 1) : rgt;
-      const float iX0 = (i > 0) ? comp(fx, i - 1) : l;
+      const float iX1 = (i < 3) ? comp(fy[q], i + 1) : rgt;
+      const float iX0 = (i > 0) ? comp(fx[q], i - 1) : l;
       float vx, vy;
-      nd[i] = apply_cell(comp(dC, i), comp(fx, i), comp(fy, i), comp(fz, i), comp(fw, i), iX1, iX0, comp(iy1, i), comp(iy0, i), c, vx, vy);
+      nd[i] = apply_cell(comp(d[q], i), comp(fx[q], i), comp(fy[q], i), comp(fz[q], i), comp(fw[q], i), iX1, iX0, comp(iy1, i),
+                         comp(iy0, i), c, vx, vy);
       if (LAST) nv[i] = pack_half2(vx, vy);
       if (EDGE && !(row_in && (unsigned)(gx0 + i) < (unsigned)g.W)) { nd[i] = 0.f; if (LAST) nv[i] = 0u; }
     }
-    if (active) {
-      if (!LAST) {
-        st4(sd + o, make_float4(nd[0], nd[1], nd[2], nd[3]));
-      } else {
-        const int lr = tc.ly0 + r;
-        if (!EDGE || (lr < g.rows && gx0 < g.pitch)) {
-          const size_t go = (size_t)((long long)lr * g.pitch) + gx0;
-          st4(out.d + go, make_float4(nd[0], nd[1], nd[2], nd[3]));
-          *reinterpret_cast<uint4*>(out.v + go) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
-        }
-      }
+    if (!LAST) {
+      d[q] = make_float4(nd[0], nd[1], nd[2], nd[3]);
+      st4(sH + oq, add4(d[q], h[q]));
+    } else {
+      const size_t go = (size_t)((long long)(tc.ly0 + r) * g.pitch) + gx0;
+      st4(out.d + go, make_float4(nd[0], nd[1], nd[2], nd[3]));
+      *reinterpret_cast<uint4*>(out.v + go) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
     }
   }
 }
 
 template <class C, bool EDGE>
 __device__ __forceinline__ void run_tile(float* st, const TileCtx& tc, const FusedOut& out, const Geom& g, const StepConsts& c, const int tid) {
-  constexpr int K = C::K;
+  constexpr int K = C::K, NG = C::NG, SX = C::SX, SY = C::SY, PLANE = C::PLANE, NT = C::NT;
+  constexpr int ITEMS = NG * (SY - 2);                 // owned items: staged rows 1..SY-2
+  constexpr int IPT = (ITEMS + NT - 1) / NT;
+  static_assert(IPT <= 2, "tile too large for the register-resident scheme");
+  static_assert(2 * NG <= NT, "halo rows are handled by the first 2*NG threads");
+  const int lane = tid & 31;
+  float* sh = st; float* sd = st + PLANE;
+  int o[IPT]; bool valid[IPT];
+  float4 h[IPT], d[IPT], fx[IPT], fy[IPT], fz[IPT], fw[IPT];
+  // ---- pull the owned items out of the landing planes; publish H = d + h -----------------------
+#pragma unroll
+  for (int q = 0; q < IPT; ++q) {
+    const int a = tid + q * NT;
+    valid[q] = a < ITEMS;
+    o[q] = (NG + (valid[q] ? a : ITEMS - 1)) * 4;      // row 1 starts NG float4 groups into the plane
+    h[q] = ld4(sh + o[q]); d[q] = ld4(sd + o[q]);
+    fx[q] = ld4(st + 2 * PLANE + o[q]); fy[q] = ld4(st + 3 * PLANE + o[q]);
+    fz[q] = ld4(st + 4 * PLANE + o[q]); fw[q] = ld4(st + 5 * PLANE + o[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < IPT; ++q)
+    if (valid[q]) st4(sd + o[q], add4(d[q], h[q]));    // each position is read and rewritten by its owner only
+  if (tid < 2 * NG) {                                  // staged rows 0 and SY-1 are never owned: H only
+    const int oh = (tid < NG ? tid : (SY - 2) * NG + tid) * 4;
+    st4(sd + oh, add4(ld4(sd + oh), ld4(sh + oh)));
+  }
+  __syncthreads();
 #pragma unroll 1
   for (int t = 1; t < K; ++t) {
-    flux_pass<C, EDGE, false>(st, 2 * (K - t) + 1, tc, out, g, c, tid);
+    flux_level<C, EDGE, false, IPT>(st, o, valid, h, d, fx, fy, fz, fw, tc, out, g, c, lane, 2 * (K - t) + 1);
     __syncthreads();
-    depth_pass<C, EDGE, false>(st, 2 * (K - t), tc, out, g, c, tid);
+    depth_level<C, EDGE, false, IPT>(st, o, valid, h, d, fx, fy, fz, fw, tc, out, g, c, lane, 2 * (K - t));
     __syncthreads();
   }
-  flux_pass<C, EDGE, true>(st, 1, tc, out, g, c, tid);
+  flux_level<C, EDGE, true, IPT>(st, o, valid, h, d, fx, fy, fz, fw, tc, out, g, c, lane, 1);
   __syncthreads();
-  depth_pass<C, EDGE, true>(st, 0, tc, out, g, c, tid);
+  depth_level<C, EDGE, true, IPT>(st, o, valid, h, d, fx, fy, fz, fw, tc, out, g, c, lane, 0);
 }
 
 template <class C>
