@@ -242,6 +242,21 @@ struct TileCtx {
 // round-trips through shared memory for its owner.
 // Passes run over all owned rows at every level: cells outside the shrinking valid region
 // hold garbage that by construction never reaches the OX x OY output centre.
+// Predicated single-instruction shared-memory accesses for the warp-edge lanes (an `if` around a
+// lone LDS/STS makes ptxas emit a divergent branch + reconvergence pair instead).
+__device__ __forceinline__ float lds_if(bool p, const float* addr, float otherwise) {
+  float v = otherwise;
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p ld.shared.f32 %0, [%1];\n}" : "+f"(v) : "r"(smem_u32(addr)), "r"((int)p));
+  return v;
+}
+__device__ __forceinline__ void sts_if(bool p, float* addr, float v) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p st.shared.f32 [%0], %1;\n}" ::"r"(smem_u32(addr)), "f"(v), "r"((int)p));
+}
+__device__ __forceinline__ void sts4_if(bool p, float* addr, float4 v) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n}" ::"r"(smem_u32(addr)), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w), "r"((int)p));
+}
+
 template <class C, bool EDGE, bool LAST, int IPT>
 __device__ __forceinline__ void flux_level(float* __restrict__ st, const int (&o)[IPT], const bool (&valid)[IPT], const float4 (&h)[IPT],
                                            const float4 (&d)[IPT], float4 (&fx)[IPT], float4 (&fy)[IPT], float4 (&fz)[IPT], float4 (&fw)[IPT],
@@ -250,6 +265,9 @@ __device__ __forceinline__ void flux_level(float* __restrict__ st, const int (&o
   constexpr int SX = C::SX, PLANE = C::PLANE;
   const float* sH = st + PLANE;
   float* sFxp = st + 2 * PLANE; float* sFxm = st + 3 * PLANE; float* sFyp = st + 4 * PLANE; float* sFym = st + 5 * PLANE;
+  float total[IPT][4], scale[IPT][4];
+  bool need = false;
+  // ---- stage A: neighbour water levels, raw outflow (no branches: the two items interleave) ----
 #pragma unroll
   for (int q = 0; q < IPT; ++q) {
     const int oq = o[q];
@@ -257,16 +275,11 @@ __device__ __forceinline__ void flux_level(float* __restrict__ st, const int (&o
     const float4 HU = ld4(sH + oq - SX), HD = ld4(sH + oq + SX);
     float HL = __shfl_up_sync(0xffffffffu, HC.w, 1);
     float HR = __shfl_down_sync(0xffffffffu, HC.x, 1);
-    if (lane == 0) HL = sH[oq - 1];
-    if (lane == 31) HR = sH[oq + 4];
+    HL = lds_if(lane == 0, sH + oq - 1, HL);
+    HR = lds_if(lane == 31, sH + oq + 4, HR);
     float* pfx = &fx[q].x; float* pfy = &fy[q].x; float* pfz = &fz[q].x; float* pfw = &fw[q].x;
     const int r = oq / SX, x = oq - r * SX;
-    // rows outside this level's margin M around the output tile feed nothing that is kept
-    if (!valid[q] || r < C::HY - M || r >= C::HY + C::OY + M) continue;
     const int gy = tc.gy0 + r, gx0 = tc.sx0 + x;
-    const bool row_in = (unsigned)gy < (unsigned)g.Hg;
-    float total[4], scale[4];
-    const float dep[4] = {d[q].x, d[q].y, d[q].z, d[q].w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float Hc = comp(HC, i);
@@ -280,27 +293,49 @@ __device__ __forceinline__ void flux_level(float* __restrict__ st, const int (&o
         if (gy + 1 >= g.Hg) hyp = Hc;
         if (gy - 1 < 0) hym = Hc;
       }
-      total[i] = flux_raw(Hc, hxp, hxm, hyp, hym, pfx[i], pfy[i], pfz[i], pfw[i], c);
+      total[q][i] = flux_raw(Hc, hxp, hxm, hyp, hym, pfx[i], pfy[i], pfz[i], pfw[i], c);
+      const float dep = comp(d[q], i);
+      const bool over = total[q][i] > dep;                                           // :58
+      scale[q][i] = over ? 0.0f : 1.0f;              // a == 0 -> a/total == +0 ; total <= a -> no scaling (x*1 == x)
+      need = need || (over && dep != 0.0f);
     }
-    flux_scale4(total, dep, scale);
+  }
+  // ---- stage B: the rare IEEE divisions (a wet cell that would drain completely this step) ----
+  if (need) {
+#pragma unroll
+    for (int q = 0; q < IPT; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dep = comp(d[q], i);
+        if (total[q][i] > dep && dep != 0.0f) scale[q][i] = __fdiv_rn(dep, total[q][i]);   // :59
+      }
+  }
+  // ---- stage C: scale, publish what the neighbours need, last level: write the flux to HBM ----
+#pragma unroll
+  for (int q = 0; q < IPT; ++q) {
+    const int oq = o[q];
+    float* pfx = &fx[q].x; float* pfy = &fy[q].x; float* pfz = &fz[q].x; float* pfw = &fw[q].x;
+    const int r = oq / SX, x = oq - r * SX;
+    const int gy = tc.gy0 + r, gx0 = tc.sx0 + x;
+    const bool row_in = (unsigned)gy < (unsigned)g.Hg;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      pfx[i] = __fmul_rn(pfx[i], scale[i]); pfy[i] = __fmul_rn(pfy[i], scale[i]);
-      pfz[i] = __fmul_rn(pfz[i], scale[i]); pfw[i] = __fmul_rn(pfw[i], scale[i]);
+      pfx[i] = __fmul_rn(pfx[i], scale[q][i]); pfy[i] = __fmul_rn(pfy[i], scale[q][i]);
+      pfz[i] = __fmul_rn(pfz[i], scale[q][i]); pfw[i] = __fmul_rn(pfw[i], scale[q][i]);
       if (EDGE && !(row_in && (unsigned)(gx0 + i) < (unsigned)g.W)) { pfx[i] = 0.f; pfy[i] = 0.f; pfz[i] = 0.f; pfw[i] = 0.f; }
     }
-    {
-      st4(sFyp + oq, fz[q]); st4(sFym + oq, fw[q]);
-      if (lane == 31) sFxp[oq + 3] = fx[q].w;          // for lane 0 of the next warp
-      if (lane == 0) sFxm[oq] = fy[q].x;               // for lane 31 of the previous warp
-      if (LAST) {
-        const int lr = tc.ly0 + r;                     // local row
-        bool store = x >= C::HX && x < C::HX + C::OX && r >= C::HY && r < C::HY + C::OY;
-        if (EDGE) store = store && lr < g.rows && gx0 < g.pitch;
-        if (store) {
-          const size_t go = (size_t)((long long)lr * g.pitch) + gx0;
-          st4(out.F[0] + go, fx[q]); st4(out.F[1] + go, fy[q]); st4(out.F[2] + go, fz[q]); st4(out.F[3] + go, fw[q]);
-        }
+    // rows outside this level's margin M around the output tile feed nothing that is kept
+    const bool live = valid[q] && r >= C::HY - M && r < C::HY + C::OY + M;
+    sts4_if(live, sFyp + oq, fz[q]);
+    sts4_if(live, sFym + oq, fw[q]);
+    sts_if(live && lane == 31, sFxp + oq + 3, fx[q].w);        // for lane 0 of the next warp
+    sts_if(live && lane == 0, sFxm + oq, fy[q].x);             // for lane 31 of the previous warp
+    if (LAST) {
+      bool store = valid[q] && x >= C::HX && x < C::HX + C::OX && r >= C::HY && r < C::HY + C::OY;
+      if (EDGE) store = store && tc.ly0 + r < g.rows && gx0 < g.pitch;
+      if (store) {
+        const size_t go = (size_t)((long long)(tc.ly0 + r) * g.pitch) + gx0;
+        st4(out.F[0] + go, fx[q]); st4(out.F[1] + go, fy[q]); st4(out.F[2] + go, fz[q]); st4(out.F[3] + go, fw[q]);
       }
     }
   }
@@ -321,18 +356,10 @@ __device__ __forceinline__ void depth_level(float* __restrict__ st, const int (&
     const float4 iy0 = ld4(sFyp + oq - SX);            // F(x,y-1).z, :35
     float l = __shfl_up_sync(0xffffffffu, fx[q].w, 1);       // F(x-1,y).x, :33
     float rgt = __shfl_down_sync(0xffffffffu, fy[q].x, 1);   // F(x+1,y).y, :32
-    if (lane == 0) l = sFxp[oq - 1];
-    if (lane == 31) rgt = sFxm[oq + 4];
+    l = lds_if(lane == 0, sFxp + oq - 1, l);
+    rgt = lds_if(lane == 31, sFxm + oq + 4, rgt);
     const int r = oq / SX, x = oq - r * SX;
     const int gy = tc.gy0 + r, gx0 = tc.sx0 + x;
-    bool store = false;
-    if (LAST) {
-      store = valid[q] && x >= C::HX && x < C::HX + C::OX && r >= C::HY && r < C::HY + C::OY;
-      if (EDGE) store = store && tc.ly0 + r < g.rows && gx0 < g.pitch;
-      if (!store) continue;
-    } else if (!valid[q] || r < C::HY - M || r >= C::HY + C::OY + M) {
-      continue;
-    }
     const bool row_in = (unsigned)gy < (unsigned)g.Hg;
     float nd[4]; uint32_t nv[4];
 #pragma unroll
@@ -346,12 +373,17 @@ __device__ __forceinline__ void depth_level(float* __restrict__ st, const int (&
       if (EDGE && !(row_in && (unsigned)(gx0 + i) < (unsigned)g.W)) { nd[i] = 0.f; if (LAST) nv[i] = 0u; }
     }
     if (!LAST) {
+      const bool live = valid[q] && r >= C::HY - M && r < C::HY + C::OY + M;
       d[q] = make_float4(nd[0], nd[1], nd[2], nd[3]);
-      st4(sH + oq, add4(d[q], h[q]));
+      sts4_if(live, sH + oq, add4(d[q], h[q]));
     } else {
-      const size_t go = (size_t)((long long)(tc.ly0 + r) * g.pitch) + gx0;
-      st4(out.d + go, make_float4(nd[0], nd[1], nd[2], nd[3]));
-      *reinterpret_cast<uint4*>(out.v + go) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+      bool store = valid[q] && x >= C::HX && x < C::HX + C::OX && r >= C::HY && r < C::HY + C::OY;
+      if (EDGE) store = store && tc.ly0 + r < g.rows && gx0 < g.pitch;
+      if (store) {
+        const size_t go = (size_t)((long long)(tc.ly0 + r) * g.pitch) + gx0;
+        st4(out.d + go, make_float4(nd[0], nd[1], nd[2], nd[3]));
+        *reinterpret_cast<uint4*>(out.v + go) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+      }
     }
   }
 }
