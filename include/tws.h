@@ -163,6 +163,12 @@ tws_status tws_advance(tws_sim* s, double frame_seconds, uint32_t* steps_done);
 /* fp64 sum of the water depth over the sim's own rows (volume check). Synchronises. */
 tws_status tws_total_volume(tws_sim* s, double* volume);
 tws_status tws_sync(tws_sim* s);
+/* Diagnostic for mass ledgers on the open (reference) boundary: fp64 sum of the outflow currently
+ * stored in the flux field that points OUT of the global grid through this sim's part of the edge
+ * (+X at x = width-1, -X at x = 0, -Y on global row 0, +Y on the last global row).  Multiplied by
+ * cell_area_inv_time_scaled it is the volume the last step drained off the map
+ * (flowApply.comp:38-41 with the exterior reading 0).  Synchronises. */
+tws_status tws_boundary_outflow(tws_sim* s, double* flux_sum);
 
 /* Device-side timing of the most recent tws_step/tws_advance batch (CUDA events on the
  * launching stream; replaces gl::TimerQuery around PerformSimulationStep,

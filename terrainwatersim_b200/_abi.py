@@ -94,6 +94,7 @@ SYMBOLS = {
     "tws_advance": (C.c_int, [_SIM, C.c_double, C.POINTER(C.c_uint32)]),
     "tws_total_volume": (C.c_int, [_SIM, C.POINTER(C.c_double)]),
     "tws_sync": (C.c_int, [_SIM]),
+    "tws_boundary_outflow": (C.c_int, [_SIM, C.POINTER(C.c_double)]),
     "tws_elapsed_ms": (C.c_int, [_SIM, C.POINTER(C.c_float)]),
     "tws_kernel_launches": (C.c_uint64, [_SIM]),
     "tws_device_view": (C.c_int, [_SIM, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),

@@ -164,6 +164,33 @@ cudaError_t launch_volume(const Geom& g, const float* d, double* partials, int n
   return cudaGetLastError();
 }
 
+// ---- outflow through the global edge (mass ledger on the open boundary) ------------------------------
+__global__ void __launch_bounds__(256) boundary_outflow_kernel(Geom g, const float* __restrict__ Fxp, const float* __restrict__ Fxm,
+                                                               const float* __restrict__ Fyp, const float* __restrict__ Fym, double* out) {
+  double acc = 0.0;
+  for (int r = threadIdx.x; r < g.rows; r += blockDim.x) {
+    const long long o = (long long)r * g.pitch;
+    acc += (double)Fxp[o + g.W - 1] + (double)Fxm[o];
+  }
+  if (g.row0 == 0)
+    for (int x = threadIdx.x; x < g.W; x += blockDim.x) acc += (double)Fym[x];
+  if (g.row0 + g.rows == g.Hg)
+    for (int x = threadIdx.x; x < g.W; x += blockDim.x) acc += (double)Fyp[(long long)(g.rows - 1) * g.pitch + x];
+  __shared__ double sm[256];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sm[0];
+}
+cudaError_t launch_boundary_outflow(const Geom& g, const Planes& p, int side, double* out, cudaStream_t st) {
+  const size_t off = (size_t)TWS_HALO_ROWS * g.pitch;
+  boundary_outflow_kernel<<<1, 256, 0, st>>>(g, p.F[side][0] + off, p.F[side][1] + off, p.F[side][2] + off, p.F[side][3] + off, out);
+  return cudaGetLastError();
+}
+
 // ---- strip exchange: push edge rows into the neighbours' halo rows over NVLink ----------------
 __global__ void __launch_bounds__(256) row_copy_kernel(RowCopy a, RowCopy b, int ncopies) {
   const RowCopy& c = (blockIdx.z == 0) ? a : b;

@@ -563,6 +563,18 @@ tws_status tws_total_volume(tws_sim* s, double* volume) {
   return TWS_OK;
 }
 
+tws_status tws_boundary_outflow(tws_sim* s, double* flux_sum) {
+  if (!s || !flux_sum) return TWS_ERR_INVALID;
+  DeviceGuard guard(s->prm.device);
+  tws_status r = sync_all(s);
+  if (r) return r;
+  TWS_CUDA(s, launch_boundary_outflow(s->geom, s->planes, s->cur, s->partials, s->st_main));
+  s->launches += 1;
+  TWS_CUDA(s, cudaMemcpyAsync(flux_sum, s->partials, sizeof(double), cudaMemcpyDeviceToHost, s->st_main));
+  TWS_CUDA(s, cudaStreamSynchronize(s->st_main));
+  return TWS_OK;
+}
+
 tws_status tws_sync(tws_sim* s) {
   if (!s) return TWS_ERR_INVALID;
   DeviceGuard guard(s->prm.device);

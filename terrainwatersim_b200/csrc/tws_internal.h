@@ -80,6 +80,7 @@ cudaError_t launch_scene(const Geom& g, const Planes& p, int side, const float* 
                          float persistence, cudaStream_t st);
 cudaError_t launch_pack_flux(const Geom& g, const Planes& p, int side, float* aos, int lr0, int nrows, bool to_aos, cudaStream_t st);
 cudaError_t launch_pack_info(const Geom& g, const Planes& p, int side, float* aos, int lr0, int nrows, bool to_aos, cudaStream_t st);
+cudaError_t launch_boundary_outflow(const Geom& g, const Planes& p, int side, double* out, cudaStream_t st);
 cudaError_t launch_volume(const Geom& g, const float* d, double* partials, int nblocks, cudaStream_t st);
 // copy `nrows` plane rows of `nplanes` planes: dst[i] + dst_row*pitch <- src[i] + src_row*pitch
 struct RowCopy { const float* src[6]; float* dst[6]; int nplanes; int src_row; int dst_row; int nrows; int pitch; };

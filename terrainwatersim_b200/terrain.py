@@ -141,6 +141,12 @@ class Terrain:
         self._check(self._lib.tws_total_volume(self._sim, C.byref(v)))
         return float(v.value)
 
+    def boundary_outflow(self) -> float:
+        """fp64 sum of the flux leaving the global grid through this strip's edge cells."""
+        v = C.c_double(0)
+        self._check(self._lib.tws_boundary_outflow(self._sim, C.byref(v)))
+        return float(v.value)
+
     _SHAPES = {
         _abi.FIELD_TERRAIN: (np.float32, ()),
         _abi.FIELD_WATER: (np.float32, ()),

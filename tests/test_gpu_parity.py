@@ -234,6 +234,28 @@ def test_reference_interface_frame_loop(tws, oracle):
         assert_state_equal(sim, tws, t, f, v, "frame loop")
 
 
+def test_boundary_outflow_ledger_matches_oracle(tws, oracle):
+    """Mass ledger on the open boundary: volume change per step == -(outflow through the edge) * areaInv,
+    with the outflow read from the flux field exactly as the oracle sums it."""
+    W, H = 96, 80
+    h, d = dam_break(W, H, rim=False)
+    c = oracle.derive_consts(float(W), W)
+    t, f, v = new_state(h, d)
+    with make_sim(tws, W, H, tws.BACKEND_FUSED, 1) as sim:
+        sim.upload(tws.FIELD_TERRAIN, h); sim.upload(tws.FIELD_WATER, d)
+        vol = sim.total_volume()
+        lost = 0.0
+        for _ in range(40):
+            sim.step(1)
+            oracle.step(t, f, v, c, 1)
+            want = (f[:, -1, 0].sum(dtype=np.float64) + f[:, 0, 1].sum(dtype=np.float64) + f[-1, :, 2].sum(dtype=np.float64) + f[0, :, 3].sum(dtype=np.float64))
+            got = sim.boundary_outflow()
+            assert got == pytest.approx(float(want), rel=1e-12, abs=1e-12)
+            lost += got * float(c[2])
+        assert lost > 0
+        assert abs((vol - sim.total_volume()) - lost) / vol < 1e-6
+
+
 def test_parameter_validation_on_device(tws):
     with make_sim(tws, 64, 64, tws.BACKEND_FUSED, 1) as sim:
         for call in (lambda: sim.SetSimulationStepsPerSecond(0.0), lambda: sim.SetFlowDamping(-1.0), lambda: sim.SetFlowAcceleration(float("nan")),
