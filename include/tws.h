@@ -43,13 +43,16 @@ typedef enum tws_status {
   TWS_ERR_UNSUPPORTED = -5  /* feature compiled out (e.g. GL interop)             */
 } tws_status;
 
-/* Which kernels run a step.  All three produce bit-identical state. */
+/* Which kernels run a step.  All of them produce bit-identical state. */
 typedef enum tws_backend {
   TWS_BACKEND_UNFUSED = 1,  /* two kernels per step, mirroring the two dispatches of
                                Terrain.cpp:255-264 (in-place, no shared memory)          */
   TWS_BACKEND_FUSED = 2,    /* one TMA-staged shared-memory stencil kernel per step      */
-  TWS_BACKEND_FUSED_TB = 3  /* fused + temporal blocking: `temporal_block` steps per HBM
-                               round trip                                                */
+  TWS_BACKEND_FUSED_TB = 3, /* fused + temporal blocking: `temporal_block` steps per HBM
+                               round trip, overlapped square tiles (halo rows recomputed) */
+  TWS_BACKEND_STREAM_TB = 4 /* fused + temporal blocking as a row-streaming pipeline: one warp
+                               per grid row, rows skewed in time instead of recomputed,
+                               `temporal_block` steps per HBM round trip                  */
 } tws_backend;
 
 typedef enum tws_boundary {
@@ -86,7 +89,7 @@ typedef struct tws_params {
   float    flow_acceleration; /* Terrain::SetFlowAcceleration,   default 10                  */
   int32_t  boundary;          /* tws_boundary                                                */
   int32_t  backend;           /* tws_backend                                                 */
-  int32_t  temporal_block;    /* steps fused per launch for FUSED_TB (1..4); ignored otherwise */
+  int32_t  temporal_block;    /* steps fused per launch for FUSED_TB / STREAM_TB (1..4); ignored otherwise */
   int32_t  device;            /* CUDA device ordinal                                         */
   float    rain_rate;         /* EXTENSION: uniform depth added per second (0 = off)         */
   float    evaporation_rate;  /* EXTENSION: uniform depth removed per second (0 = off)       */

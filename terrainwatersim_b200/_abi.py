@@ -20,6 +20,7 @@ TWS_ERR_UNSUPPORTED = -5
 BACKEND_UNFUSED = 1
 BACKEND_FUSED = 2
 BACKEND_FUSED_TB = 3
+BACKEND_STREAM_TB = 4
 
 BOUNDARY_REFERENCE_OPEN = 0
 BOUNDARY_CLOSED = 1

@@ -17,82 +17,9 @@
 //       OX x OY centre straight from registers (flux after the last flux pass, depth and
 //       velocity after the last depth pass).  HBM traffic per cell: 24 B read + 24 B
 //       written per K cell-updates (+ halo over-fetch, mostly served by L2).
-#include "tws_internal.h"
-
-#include <cuda_fp16.h>
+#include "cell_math.cuh"
 
 namespace tws {
-
-// ------------------------------------------------------------------------------------
-// cell arithmetic shared by all kernels
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ float max0(float v) { return (v > 0.0f) ? v : 0.0f; }   // flowUpdate.comp:54
-
-// flowUpdate.comp:44-57 for one cell.  f* in: old outflow, out: clamped-at-zero new outflow
-// BEFORE the "cannot drain below zero" scaling; returns total = (sum f') * areaInv (:57).
-__device__ __forceinline__ float flux_raw(float Hc, float Hxp, float Hxm, float Hyp, float Hym,
-                                          float& fx, float& fy, float& fz, float& fw, const StepConsts& c) {
-  float nx = Hc - Hxp, ny = Hc - Hxm, nz = Hc - Hyp, nw = Hc - Hym;                  // :44-47
-  nx = __fadd_rn(__fmul_rn(fx, c.friction), __fmul_rn(nx, c.accel));                 // :53
-  ny = __fadd_rn(__fmul_rn(fy, c.friction), __fmul_rn(ny, c.accel));
-  nz = __fadd_rn(__fmul_rn(fz, c.friction), __fmul_rn(nz, c.accel));
-  nw = __fadd_rn(__fmul_rn(fw, c.friction), __fmul_rn(nw, c.accel));
-  fx = max0(nx); fy = max0(ny); fz = max0(nz); fw = max0(nw);                        // :54
-  return __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(fx, fy), fz), fw), c.area_inv);     // :57
-}
-
-// flowUpdate.comp:58-59 for the four cells of one float4 group: if (total > a) f' *= a / total.
-// The IEEE division is needed only for a wet cell that would drain completely this step —
-// rare — so the common path is branch free: scale = 1 when total <= a (x*1 == x bit for bit,
-// the shader does not multiply at all there), scale = 0 when a == 0 (0/total == +0 for every
-// total > 0), and ONE warp-level branch covers the cells that really divide.
-__device__ __forceinline__ void flux_scale4(const float (&total)[4], const float (&depth)[4], float (&s)[4]) {
-  bool need = false;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool over = total[i] > depth[i];
-    const bool dry = depth[i] == 0.0f;
-    s[i] = over ? 0.0f : 1.0f;
-    need = need || (over && !dry);
-  }
-  if (need) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (total[i] > depth[i] && depth[i] != 0.0f) s[i] = __fdiv_rn(depth[i], total[i]);
-  }
-}
-
-// Scalar form used by the unfused baseline.
-__device__ __forceinline__ void flux_cell(float Hc, float Hxp, float Hxm, float Hyp, float Hym, float depth,
-                                          float& fx, float& fy, float& fz, float& fw, const StepConsts& c) {
-  const float total = flux_raw(Hc, Hxp, Hxm, Hyp, Hym, fx, fy, fz, fw, c);
-  if (total > depth) {                                                               // :58
-    const float s = (depth == 0.0f) ? 0.0f : __fdiv_rn(depth, total);                // :59
-    fx = __fmul_rn(fx, s); fy = __fmul_rn(fy, s); fz = __fmul_rn(fz, s); fw = __fmul_rn(fw, s);
-  }
-}
-
-// flowApply.comp:38-46.  Returns the new depth; vx, vy the flow vector.
-__device__ __forceinline__ float apply_cell(float depth, float fx, float fy, float fz, float fw, float iX1, float iX0,
-                                            float iY1, float iY0, const StepConsts& c, float& vx, float& vy) {
-  const float in = __fadd_rn(__fadd_rn(__fadd_rn(iX1, iX0), iY1), iY0);              // :38
-  const float out = __fadd_rn(__fadd_rn(__fadd_rn(fx, fy), fz), fw);                 // :39
-  float nd = max0(__fadd_rn(depth, __fmul_rn(__fsub_rn(in, out), c.area_inv)));      // :41
-  if (c.ext_sources) nd = max0(__fsub_rn(__fadd_rn(nd, c.rain_step), c.evap_step));  // EXT
-  vx = __fsub_rn(__fsub_rn(iX1, fx), __fsub_rn(iX0, fy));                            // :45
-  vy = __fsub_rn(__fsub_rn(iY1, fz), __fsub_rn(iY0, fw));                            // :46
-  return nd;
-}
-
-__device__ __forceinline__ uint32_t pack_half2(float x, float y) {                  // rg16f store, :52
-  const __half2 h = __floats2half2_rn(x, y);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
 // ------------------------------------------------------------------------------------
 // unfused baseline: one thread per 4 consecutive cells, float4 global access
@@ -174,31 +101,6 @@ __global__ void __launch_bounds__(256) unfused_apply_kernel(Geom g, float* d, co
 // ------------------------------------------------------------------------------------
 // fused / temporally blocked kernel
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
-}
-
 // Tile configuration of the pipelined kernel.  One persistent CTA per SM owns TWO staging
 // buffers: while the passes run on tile j in one buffer the TMA unit fills the other with
 // tile j+1, so the SM never idles on the load and HBM never idles on the compute.
@@ -216,10 +118,6 @@ struct FusedCfg {
   static_assert(OX % 4 == 0 && SX <= 256 && SY <= 256, "TMA box limits");
   static_assert((PLANE * 4) % 128 == 0, "staged planes must keep 128 B alignment");
   static_assert(NT % 32 == 0, "whole warps");
-};
-
-struct FusedOut {          // plane pointers at local row 0
-  float* d; float* F[4]; uint32_t* v;
 };
 
 struct TileCtx {
@@ -587,21 +485,19 @@ static void box_for(int K, int* sx, int* sy) {
   }
 }
 
-// Descriptors for reading side `side` with the K-level kernel.  The tensor covers the
+// Descriptors for reading side `side` with boxes of box_x x box_y cells.  The tensor covers the
 // rows that hold real data: own rows plus the halo rows towards an existing neighbour;
 // everything outside is the global exterior and is zero-filled by the TMA unit.
-cudaError_t fused_build_tma(int K, const Geom& g, const Planes& p, int side, TmaSet* out, std::string* err) {
+cudaError_t build_tma_boxes(const Geom& g, const Planes& p, int side, int box_x, int box_y, TmaSet* out, std::string* err) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { if (err) *err = "cuTensorMapEncodeTiled not available from the driver"; return cudaErrorNotSupported; }
-  int sx, sy;
-  box_for(K, &sx, &sy);
   const int first_row = g.has_up ? 0 : TWS_HALO_ROWS;   // plane row of the first visible row
   const int vis_rows = g.rows + (g.has_up ? TWS_HALO_ROWS : 0) + (g.has_down ? TWS_HALO_ROWS : 0);
   float* bases[6] = {p.h, p.d[side], p.F[side][0], p.F[side][1], p.F[side][2], p.F[side][3]};
   for (int i = 0; i < 6; ++i) {
     cuuint64_t dims[2] = {(cuuint64_t)g.W, (cuuint64_t)vis_rows};
     cuuint64_t strides[1] = {(cuuint64_t)g.pitch * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)sx, (cuuint32_t)sy};
+    cuuint32_t box[2] = {(cuuint32_t)box_x, (cuuint32_t)box_y};
     cuuint32_t estr[2] = {1, 1};
     void* base = bases[i] + (size_t)first_row * g.pitch;
     CUresult r = enc(&out->m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -612,6 +508,12 @@ cudaError_t fused_build_tma(int K, const Geom& g, const Planes& p, int side, Tma
     }
   }
   return cudaSuccess;
+}
+
+cudaError_t fused_build_tma(int K, const Geom& g, const Planes& p, int side, TmaSet* out, std::string* err) {
+  int sx, sy;
+  box_for(K, &sx, &sy);
+  return build_tma_boxes(g, p, side, sx, sy, out, err);
 }
 
 // ---- unfused launchers -------------------------------------------------------------------

@@ -46,6 +46,8 @@ struct tws_sim {
   int K = 1;                         // steps per launch
   TmaSet tma[TWS_MAX_TB + 1][2];     // [k][side]
   bool tma_ready[TWS_MAX_TB + 1] = {};
+  TmaSet tma_stream[2];              // row descriptors of the streaming pipeline, [side]
+  bool tma_stream_ready = false;
   cudaStream_t st_main = nullptr, st_edge = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_main = nullptr, ev_edge = nullptr;
   bool timed = false;
@@ -133,6 +135,17 @@ tws_status ensure_tma(tws_sim* s, int k) {
   return TWS_OK;
 }
 
+tws_status ensure_tma_stream(tws_sim* s) {
+  if (s->tma_stream_ready) return TWS_OK;
+  for (int side = 0; side < 2; ++side) {
+    std::string e;
+    cudaError_t r = stream_build_tma(s->geom, s->planes, side, &s->tma_stream[side], &e);
+    if (r != cudaSuccess) return fail(s, TWS_ERR_CUDA, e.empty() ? std::string("building TMA descriptors failed") : e);
+  }
+  s->tma_stream_ready = true;
+  return TWS_OK;
+}
+
 tws_status ensure_staging(tws_sim* s, size_t bytes) {
   if (s->staging_bytes >= bytes) return TWS_OK;
   if (s->staging) cudaFree(s->staging);
@@ -186,6 +199,41 @@ tws_status post_and_count(tws_sim* s, cudaStream_t st) {
   return TWS_OK;
 }
 
+// One block of k steps of the row-streaming pipeline.  A strip runs the rows that neither depend on
+// a halo nor are pushed to a neighbour (all but the outer TWS_HALO_ROWS) on the main stream and the
+// two edge bands on the edge stream behind the neighbours' flags, exactly like the tile engine.
+tws_status run_block_stream(tws_sim* s, int k) {
+  const Geom& g = s->geom;
+  const bool strip = g.has_up || g.has_down;
+  const int src = s->cur;
+  tws_status r = ensure_tma_stream(s);
+  if (r) return r;
+  if (!strip) {
+    TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, g.rows, s->st_main));
+    s->launches += 1;
+    s->cur = 1 - src;
+    return TWS_OK;
+  }
+  int e_top = g.has_up ? TWS_HALO_ROWS : 0, e_bot = g.has_down ? TWS_HALO_ROWS : 0;
+  if (e_top + e_bot >= g.rows) { e_top = g.rows; e_bot = 0; }
+  const int i0 = e_top, i1 = g.rows - e_bot;
+  TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));
+  if (i1 > i0) {
+    TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i0, i1, s->st_main));
+    s->launches += 1;
+  }
+  TWS_CUDA(s, cudaStreamWaitEvent(s->st_edge, s->ev_main, 0));
+  TWS_CUDA(s, launch_wait_flags(s->ctrl, g.has_up, g.has_down, s->epoch, s->st_edge)); s->launches++;
+  if (e_top > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, e_top, s->st_edge)); s->launches++; }
+  if (e_bot > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i1, g.rows, s->st_edge)); s->launches++; }
+  r = push_edges(s, 1 - src, false, s->st_edge); if (r) return r;
+  r = post_and_count(s, s->st_edge); if (r) return r;
+  TWS_CUDA(s, cudaEventRecord(s->ev_edge, s->st_edge));
+  TWS_CUDA(s, cudaEventRecord(s->ev_main, s->st_main));
+  s->cur = 1 - src;
+  return TWS_OK;
+}
+
 // One block of k fused steps (or one unfused step) including the strip exchange.
 tws_status run_block(tws_sim* s, int k) {
   const Geom& g = s->geom;
@@ -197,6 +245,7 @@ tws_status run_block(tws_sim* s, int k) {
     s->launches += 2;
     return TWS_OK;
   }
+  if (s->prm.backend == TWS_BACKEND_STREAM_TB) return run_block_stream(s, k);
   tws_status r = ensure_tma(s, k);
   if (r) return r;
   const int tiles = fused_tile_rows(k, g.rows);
@@ -238,7 +287,7 @@ tws_status run_steps(tws_sim* s, int n) {
   const bool strip = g.has_up || g.has_down;
   if (strip && !s->connected) return fail(s, TWS_ERR_STATE, "strip sim stepped before tws_halo_connect");
   TWS_CUDA(s, cudaEventRecord(s->ev_start, s->st_main));
-  const int K = (s->prm.backend == TWS_BACKEND_FUSED_TB) ? s->K : 1;
+  const int K = (s->prm.backend == TWS_BACKEND_FUSED_TB || s->prm.backend == TWS_BACKEND_STREAM_TB) ? s->K : 1;
   while (n > 0) {
     const int k = std::min(n, K);
     tws_status r = run_block(s, k);
@@ -305,9 +354,9 @@ tws_status tws_create(const tws_params* p, tws_sim** out) {
   if (bad_float(p->flow_acceleration) || p->flow_acceleration < 0.0f) return fail(nullptr, TWS_ERR_INVALID, "tws_create: flow_acceleration must be >= 0");
   if (bad_float(p->rain_rate) || bad_float(p->evaporation_rate) || p->rain_rate < 0.0f || p->evaporation_rate < 0.0f)
     return fail(nullptr, TWS_ERR_INVALID, "tws_create: rain/evaporation must be >= 0");
-  if (p->backend < TWS_BACKEND_UNFUSED || p->backend > TWS_BACKEND_FUSED_TB) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown backend");
+  if (p->backend < TWS_BACKEND_UNFUSED || p->backend > TWS_BACKEND_STREAM_TB) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown backend");
   if (p->boundary != TWS_BOUNDARY_REFERENCE_OPEN && p->boundary != TWS_BOUNDARY_CLOSED) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown boundary");
-  if (p->backend == TWS_BACKEND_FUSED_TB && (p->temporal_block < 1 || p->temporal_block > TWS_MAX_TB))
+  if ((p->backend == TWS_BACKEND_FUSED_TB || p->backend == TWS_BACKEND_STREAM_TB) && (p->temporal_block < 1 || p->temporal_block > TWS_MAX_TB))
     return fail(nullptr, TWS_ERR_INVALID, "tws_create: temporal_block must be 1..4");
 
   int ndev = 0;
@@ -322,7 +371,7 @@ tws_status tws_create(const tws_params* p, tws_sim** out) {
   tws_sim* s = new (std::nothrow) tws_sim;
   if (!s) return fail(nullptr, TWS_ERR_NOMEM, "tws_create: out of host memory");
   s->prm = *p;
-  s->K = (p->backend == TWS_BACKEND_FUSED_TB) ? p->temporal_block : 1;
+  s->K = (p->backend == TWS_BACKEND_FUSED_TB || p->backend == TWS_BACKEND_STREAM_TB) ? p->temporal_block : 1;
   DeviceGuard guard(p->device);
   Geom& g = s->geom;
   g.W = p->width; g.Hg = p->height; g.row0 = p->row_begin; g.rows = p->row_end - p->row_begin;
