@@ -488,7 +488,7 @@ static void box_for(int K, int* sx, int* sy) {
 // Descriptors for reading side `side` with boxes of box_x x box_y cells.  The tensor covers the
 // rows that hold real data: own rows plus the halo rows towards an existing neighbour;
 // everything outside is the global exterior and is zero-filled by the TMA unit.
-cudaError_t build_tma_boxes(const Geom& g, const Planes& p, int side, int box_x, int box_y, TmaSet* out, std::string* err) {
+cudaError_t build_tma_boxes(const Geom& g, const Planes& p, int side, int box_x, int box_y, TmaSet* out, std::string* err, int l2_promotion) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { if (err) *err = "cuTensorMapEncodeTiled not available from the driver"; return cudaErrorNotSupported; }
   const int first_row = g.has_up ? 0 : TWS_HALO_ROWS;   // plane row of the first visible row
@@ -500,8 +500,10 @@ cudaError_t build_tma_boxes(const Geom& g, const Planes& p, int side, int box_x,
     cuuint32_t box[2] = {(cuuint32_t)box_x, (cuuint32_t)box_y};
     cuuint32_t estr[2] = {1, 1};
     void* base = bases[i] + (size_t)first_row * g.pitch;
+    const CUtensorMapL2promotion promo = l2_promotion == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                       : l2_promotion == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
     CUresult r = enc(&out->m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
       return cudaErrorInvalidValue;
@@ -513,7 +515,7 @@ cudaError_t build_tma_boxes(const Geom& g, const Planes& p, int side, int box_x,
 cudaError_t fused_build_tma(int K, const Geom& g, const Planes& p, int side, TmaSet* out, std::string* err) {
   int sx, sy;
   box_for(K, &sx, &sy);
-  return build_tma_boxes(g, p, side, sx, sy, out, err);
+  return build_tma_boxes(g, p, side, sx, sy, out, err, 2);
 }
 
 // ---- unfused launchers -------------------------------------------------------------------

@@ -4,35 +4,35 @@
 // contract in cell_math.cuh / DESIGN.md section 2) and bit-identical results; what differs is how K
 // whole steps are blocked over one HBM round trip:
 //
-//   * The grid is cut into column strips SXW = 256 cells wide (OX = 256 - 2*HX of them are
+//   * The grid is cut into column strips SXW = 128*G cells wide (OX = SXW - 2*HX of them are
 //     outputs, HX = x halo of the K-step dependency cone) and every strip is marched top to
 //     bottom.  A persistent CTA (one per SM) owns a contiguous piece of the (strip, row) work
 //     list; all pieces have the same number of rows, so any grid size balances over 148 SMs.
-//   * ONE WARP OWNS ONE ROW (256 cells: lane L holds the float4 groups L and L+32) for the row's
-//     whole life: the TMA unit lands the row's h, d and four flux planes in the warp's private
-//     landing buffer (6 x 1 KB, `cp.async.bulk.tensor.2d`, mbarrier completion, out-of-bounds
-//     zero fill = the reference's exterior rule), the warp pulls them into registers, and the
-//     2K half-passes (flux_1, depth_1, ... flux_K, depth_K) update them IN REGISTERS.  The
-//     moment a landing buffer has been read the same warp issues the TMA load of ITS next row
-//     (row + NW), which lands while the current row is being computed: loads never stall.
-//   * Rows are skewed in time instead of recomputed: row y can run half-pass s as soon as rows
-//     y-1 and y+1 have finished half-pass s-1.  Only what a vertical neighbour needs goes
-//     through shared memory (the water level H = d + h, the +Y and -Y outflow: 3 KB per row
-//     slot); x neighbours are adjacent lanes (warp shuffles).  Each row slot publishes a
-//     monotonically increasing progress word in shared memory (st.release / ld.acquire); a
-//     warp waits only for its two neighbours, never for the CTA — there is no __syncthreads
-//     in the row loop, and warps in different phases overlap their shared-memory and FP work.
-//   * No y-halo recomputation: each piece pays 2K warm-up rows once.  Per cell-update the
-//     kernel executes ~1/0.94 (K <= 2) or ~1/0.91 (K = 3, 4) of the minimum work, against 1/0.71
-//     for the tile kernel at K = 2, and moves 48/K B (+ x-halo re-reads) through HBM.
+//   * ONE WARP OWNS ONE ROW (lane L holds the float4 groups L, L+32, ...) for the row's whole life:
+//     the TMA unit lands the row's h, d and four flux planes in the warp's private landing buffer
+//     (`cp.async.bulk.tensor.2d`, mbarrier completion, out-of-bounds zero fill = the reference's
+//     exterior rule), the warp pulls them into registers, and the 2K half-passes (flux_1, depth_1,
+//     ... flux_K, depth_K) update them IN REGISTERS.  The moment a landing buffer has been read
+//     the same warp issues the TMA load of ITS next row (row + NW), which lands while the
+//     current row is being computed.
+//   * Rows are skewed in time instead of recomputed: row y runs half-pass s as soon as rows y-1
+//     and y+1 have finished half-pass s-1.  Only what a vertical neighbour needs goes through
+//     shared memory (the water level H = d + h, the +Y and -Y outflow: 12 B per cell and slot);
+//     x neighbours are adjacent lanes (warp shuffles).  A warp waits only for its two neighbour
+//     slots, never for the CTA: there is no __syncthreads in the row loop, and warps in
+//     different phases overlap their shared-memory, FP and store work.
+//   * No y-halo recomputation: each piece pays 2K warm-up rows once, and HBM sees 48/K B per
+//     cell-update plus the x-halo re-reads.
 #include "cell_math.cuh"
+
+#include <cstdio>
 
 namespace tws {
 
-template <int K_, int NW_>
+template <int K_, int NW_, int G_>
 struct StreamCfg {
-  static constexpr int K = K_, NW = NW_, NT = NW_ * 32;
-  static constexpr int SXW = 256;                       // staged strip width: 2 float4 groups per lane
+  static constexpr int K = K_, NW = NW_, NT = NW_ * 32, G = G_;
+  static constexpr int SXW = 128 * G;                   // staged strip width: G float4 groups per lane
   static constexpr int HX = ((2 * K + 3) / 4) * 4;      // x halo rounded to whole float4 groups
   static constexpr int OX = SXW - 2 * HX;               // output columns per strip
   static constexpr int NHP = 2 * K + 1;                 // half-passes per row, the load included
@@ -42,69 +42,153 @@ struct StreamCfg {
   static_assert(NW > 2 * K, "the row ring must be deeper than the dependency cone");
 };
 
-// ---- neighbour synchronisation -----------------------------------------------------------
-__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p) {
+// ------------------------------------------------------------------------------------------
+// Neighbour synchronisation.  Two interchangeable mechanisms (TWS_STREAM_WAIT):
+//   4 (default) — event mbarriers: one mbarrier per (slot, half-pass, ring-turn parity), arrived on
+//     once per row, so a barrier completes once every second row of its slot and its phase parity
+//     is bit 1 of the slot's ring-turn count.  A waiting warp sleeps in hardware
+//     (mbarrier.try_wait with a suspend-time hint) and costs no issue slots.  A parity wait is
+//     exact only while the awaited phase is the one in progress or the one just completed, i.e.
+//     while the neighbour slot is less than two ring turns away from the awaited row in either
+//     direction — which the dependency structure guarantees (with a single barrier per (slot,
+//     half-pass) it does not: in the first turn slot 0 can be a whole turn behind or ahead of the
+//     last slot).  Every slot arrives on all of its barriers in every ring turn of a piece, also
+//     for half-passes a row skips, so the phase counts are a pure function of the turn count and the
+//     barriers live across pieces.  tests/test_stream_protocol.py model-checks this protocol.
+//   0 — progress words: each slot publishes `rows done * NHP + half-passes done` (st.release) and
+//     a waiting warp polls its two neighbours' words (ld.acquire, broadcast LDS).
+// ------------------------------------------------------------------------------------------
+#ifndef TWS_STREAM_WAIT
+#define TWS_STREAM_WAIT 4
+#endif
+#ifndef TWS_STREAM_SUSPEND_NS
+#define TWS_STREAM_SUSPEND_NS 20000
+#endif
+#ifndef TWS_STREAM_L2PROMO
+#define TWS_STREAM_L2PROMO 0   // 0: none, 1: 128 B, 2: 256 B
+#endif
+
+__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
   uint32_t v;
-  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_shared(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+__device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t addr) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 
-// Every lane polls both progress words (one broadcast LDS each).  A bounded spin: a wait that
-// never completes is a bug, and a trap (launch failure on the host) is better than a hung GPU.
-__device__ __forceinline__ void wait_rows(const uint32_t* pu, uint32_t need_u, const uint32_t* pd, uint32_t need_d) {
-  uint32_t spins = 0;
-  while (ld_acquire_shared(pu) < need_u || ld_acquire_shared(pd) < need_d) {
-    if (++spins > (1u << 27)) __trap();
+// Per-row synchronisation cursor: advanced by one half-pass per wait() / signal().
+struct RowSync {
+  uint32_t up, dn, me;    // shared-memory addresses: neighbours' event barrier (or progress word), own
+  uint32_t pu, pd;        // mode 4: awaited phase parities; mode 0: awaited progress values
+  uint32_t val;           // mode 0: own next progress value
+  bool up_on;             // false for the first row of a piece (nobody above)
+
+  // rows idx-1 and idx+1 have finished the half-pass before the one about to run
+  __device__ __forceinline__ void wait() {
+    uint32_t spins = 0;
+#if TWS_STREAM_WAIT == 4
+    uint32_t done;
+    const uint32_t a = up_on ? up : dn, pa = up_on ? pu : pd;
+    do {
+      asm volatile(
+          "{\n"
+          ".reg .pred p, q;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %5;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4, %5;\n"
+          "and.pred p, p, q;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}\n" : "=r"(done) : "r"(a), "r"(pa), "r"(dn), "r"(pd), "r"((uint32_t)TWS_STREAM_SUSPEND_NS) : "memory");
+      if (!done && ++spins > (1u << 20)) __trap();      // a wait that never completes is a bug; a trap beats a hung GPU
+    } while (!done);
+    up += 16; dn += 16;                                  // evt[slot][s][turn & 1] -> evt[slot][s + 1][turn & 1]
+#else
+    while ((up_on && ld_acquire_shared(up) < pu) || ld_acquire_shared(dn) < pd) {
+      if (++spins > (1u << 27)) __trap();
+    }
+    ++pu; ++pd;
+#endif
+    __syncwarp();
   }
-  __syncwarp();
-}
-__device__ __forceinline__ void signal_row(uint32_t* p, uint32_t value, int lane) {
-  __syncwarp();                                   // every lane's shared-memory stores are ordered before ...
-  if (lane == 0) st_release_shared(p, value);     // ... the release of the new progress value
-}
-
-struct RowCtx {
-  int gy;          // global row
-  int gxa, gxb;    // global x of the lane's two groups
-  bool row_in;     // the row exists in the global grid
-  bool store;      // the row is an output row of this piece
-  bool sta, stb;   // the lane's groups are output columns
-  size_t goa, gob; // element offsets of the two groups in the output planes
+  // this row has finished a half-pass: every lane's shared-memory stores are ordered before the release
+  __device__ __forceinline__ void signal(int lane) {
+    __syncwarp();
+#if TWS_STREAM_WAIT == 4
+    if (lane == 0) mbar_arrive(me);
+    me += 16;
+#else
+    if (lane == 0) st_release_shared(me, val);
+    ++val;
+#endif
+  }
 };
 
-// x neighbours of the lane's two groups.  `w3` / `x0`: component 3 / 0 of the value in groups
-// (a, b).  left(a) = lane-1's a.w, left(b) = lane-1's b.w but lane 0 takes lane 31's a.w;
-// right(a) = lane+1's a.x but lane 31 takes lane 0's b.x, right(b) = lane+1's b.x.  The two
-// strip-edge cells get their own value back: they lie in the x halo, whose results are never kept.
-__device__ __forceinline__ void x_neighbours(float aw, float bw, float ax, float bx, int lane, float& la, float& lb, float& ra, float& rb) {
-  la = __shfl_up_sync(0xffffffffu, aw, 1);
-  lb = __shfl_sync(0xffffffffu, lane == 31 ? aw : bw, (lane + 31) & 31);
-  ra = __shfl_sync(0xffffffffu, lane == 0 ? bx : ax, (lane + 1) & 31);
-  rb = __shfl_down_sync(0xffffffffu, bx, 1);
+template <int G>
+struct RowCtx {
+  int gy;          // global row
+  int gx[G];       // global x of the lane's groups
+  bool row_in;     // the row exists in the global grid
+  bool store;      // the row is an output row of this piece
+  bool st[G];      // the lane's groups are output columns
+  size_t go[G];    // element offsets of the groups in the output planes
+};
+
+// x neighbours of the lane's groups; `w3` / `x0` are component 3 / 0 of the value in each group.
+// Lane L owns groups L (and L+32 when G = 2), so left(a) = lane-1's a.w, left(b) = lane-1's b.w but
+// lane 0 takes lane 31's a.w; right(a) = lane+1's a.x but lane 31 takes lane 0's b.x, right(b) =
+// lane+1's b.x.  The two strip-edge cells get their own value back: they lie in the x halo, whose
+// results are never kept.
+template <int G>
+__device__ __forceinline__ void x_neighbours(const float (&w3)[G], const float (&x0)[G], int lane, float (&l)[G], float (&r)[G]) {
+  if (G == 1) {
+    l[0] = __shfl_up_sync(0xffffffffu, w3[0], 1);
+    r[0] = __shfl_down_sync(0xffffffffu, x0[0], 1);
+  } else {
+    l[0] = __shfl_up_sync(0xffffffffu, w3[0], 1);
+    l[G - 1] = __shfl_sync(0xffffffffu, lane == 31 ? w3[0] : w3[G - 1], (lane + 31) & 31);
+    r[0] = __shfl_sync(0xffffffffu, lane == 0 ? x0[G - 1] : x0[0], (lane + 1) & 31);
+    r[G - 1] = __shfl_down_sync(0xffffffffu, x0[G - 1], 1);
+  }
 }
 
-// flowUpdate.comp:34-62 for the lane's 8 cells.  Reads the neighbour rows' water level, leaves the
+// flowApply.comp:38-46 with the source/sink extension compiled in or out.
+template <bool EXT>
+__device__ __forceinline__ float apply_cell_t(float depth, float fx, float fy, float fz, float fw, float iX1, float iX0, float iY1,
+                                              float iY0, const StepConsts& c, float& vx, float& vy) {
+  const float in = __fadd_rn(__fadd_rn(__fadd_rn(iX1, iX0), iY1), iY0);              // :38
+  const float out = __fadd_rn(__fadd_rn(__fadd_rn(fx, fy), fz), fw);                 // :39
+  float nd = max0(__fadd_rn(depth, __fmul_rn(__fsub_rn(in, out), c.area_inv)));      // :41
+  if (EXT) nd = max0(__fsub_rn(__fadd_rn(nd, c.rain_step), c.evap_step));            // EXT (same expression as apply_cell)
+  vx = __fsub_rn(__fsub_rn(iX1, fx), __fsub_rn(iX0, fy));                            // :45
+  vy = __fsub_rn(__fsub_rn(iY1, fz), __fsub_rn(iY0, fw));                            // :46
+  return nd;
+}
+
+// flowUpdate.comp:34-62 for the lane's 4*G cells.  Reads the neighbour rows' water level, leaves the
 // new outflow in registers, publishes its +-Y components; LAST also stores the flux planes to HBM.
-template <bool EDGE, bool LAST>
-__device__ __forceinline__ void stream_flux(const float* __restrict__ sHup, const float* __restrict__ sHdn, float* __restrict__ sFyp,
-                                            float* __restrict__ sFym, const int oa, const int ob, const float4 (&h)[2], const float4 (&d)[2],
-                                            float4 (&fx)[2], float4 (&fy)[2], float4 (&fz)[2], float4 (&fw)[2], const RowCtx& rc,
-                                            const FusedOut& out, const Geom& g, const StepConsts& c, const int lane) {
-  float4 HC[2], HU[2], HD[2];
-  HC[0] = add4(d[0], h[0]); HC[1] = add4(d[1], h[1]);                                // a + r, flowUpdate.comp:34
-  HU[0] = ld4(sHup + oa); HU[1] = ld4(sHup + ob);
-  HD[0] = ld4(sHdn + oa); HD[1] = ld4(sHdn + ob);
-  float HL[2], HR[2];
-  x_neighbours(HC[0].w, HC[1].w, HC[0].x, HC[1].x, lane, HL[0], HL[1], HR[0], HR[1]);
-  float total[2][4], scale[2][4];
+// The three slot pointers address this lane's first group in plane 0 (H) of the slot.
+template <int G, int SXW, bool EDGE, bool LAST>
+__device__ __forceinline__ void stream_flux(const float* __restrict__ up, const float* __restrict__ dn, float* __restrict__ me, const int lane,
+                                            const float4 (&h)[G], const float4 (&d)[G], float4 (&fx)[G], float4 (&fy)[G], float4 (&fz)[G],
+                                            float4 (&fw)[G], const RowCtx<G>& rc, const FusedOut& out, const Geom& g, const StepConsts& c) {
+  float4 HC[G], HU[G], HD[G];
+  float w3[G], x0[G], HL[G], HR[G];
+#pragma unroll
+  for (int q = 0; q < G; ++q) {
+    HC[q] = add4(d[q], h[q]);                                                        // a + r, flowUpdate.comp:34
+    HU[q] = ld4(up + 128 * q);
+    HD[q] = ld4(dn + 128 * q);
+    w3[q] = HC[q].w; x0[q] = HC[q].x;
+  }
+  x_neighbours<G>(w3, x0, lane, HL, HR);
+  float total[G][4], scale[G][4];
   bool need = false;
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < G; ++q) {
     float* pfx = &fx[q].x; float* pfy = &fy[q].x; float* pfz = &fz[q].x; float* pfw = &fw[q].x;
-    const int gx0 = q ? rc.gxb : rc.gxa;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float Hc = comp(HC[q], i);
@@ -112,7 +196,7 @@ __device__ __forceinline__ void stream_flux(const float* __restrict__ sHup, cons
       float hxm = (i > 0) ? comp(HC[q], i - 1) : HL[q];
       float hyp = comp(HD[q], i), hym = comp(HU[q], i);
       if (EDGE && c.closed) {
-        const int gx = gx0 + i;
+        const int gx = rc.gx[q] + i;
         if (gx + 1 >= g.W) hxp = Hc;
         if (gx - 1 < 0) hxm = Hc;
         if (rc.gy + 1 >= g.Hg) hyp = Hc;
@@ -127,7 +211,7 @@ __device__ __forceinline__ void stream_flux(const float* __restrict__ sHup, cons
   }
   if (need) {                                    // the rare IEEE divisions: a wet cell that would drain completely
 #pragma unroll
-    for (int q = 0; q < 2; ++q)
+    for (int q = 0; q < G; ++q)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float dep = comp(d[q], i);
@@ -135,64 +219,64 @@ __device__ __forceinline__ void stream_flux(const float* __restrict__ sHup, cons
       }
   }
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < G; ++q) {
     float* pfx = &fx[q].x; float* pfy = &fy[q].x; float* pfz = &fz[q].x; float* pfw = &fw[q].x;
-    const int gx0 = q ? rc.gxb : rc.gxa;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       pfx[i] = __fmul_rn(pfx[i], scale[q][i]); pfy[i] = __fmul_rn(pfy[i], scale[q][i]);
       pfz[i] = __fmul_rn(pfz[i], scale[q][i]); pfw[i] = __fmul_rn(pfw[i], scale[q][i]);
-      if (EDGE && !(rc.row_in && (unsigned)(gx0 + i) < (unsigned)g.W)) { pfx[i] = 0.f; pfy[i] = 0.f; pfz[i] = 0.f; pfw[i] = 0.f; }
+      if (EDGE && !(rc.row_in && (unsigned)(rc.gx[q] + i) < (unsigned)g.W)) { pfx[i] = 0.f; pfy[i] = 0.f; pfz[i] = 0.f; pfw[i] = 0.f; }
     }
-  }
-  st4(sFyp + oa, fz[0]); st4(sFyp + ob, fz[1]);
-  st4(sFym + oa, fw[0]); st4(sFym + ob, fw[1]);
-  if (LAST && rc.store) {
-    if (rc.sta) { st4(out.F[0] + rc.goa, fx[0]); st4(out.F[1] + rc.goa, fy[0]); st4(out.F[2] + rc.goa, fz[0]); st4(out.F[3] + rc.goa, fw[0]); }
-    if (rc.stb) { st4(out.F[0] + rc.gob, fx[1]); st4(out.F[1] + rc.gob, fy[1]); st4(out.F[2] + rc.gob, fz[1]); st4(out.F[3] + rc.gob, fw[1]); }
+    st4(me + SXW + 128 * q, fz[q]);              // plane 1: +Y outflow, read by the row below
+    st4(me + 2 * SXW + 128 * q, fw[q]);          // plane 2: -Y outflow, read by the row above
+    if (LAST && rc.store && rc.st[q]) {
+      st4(out.F[0] + rc.go[q], fx[q]); st4(out.F[1] + rc.go[q], fy[q]); st4(out.F[2] + rc.go[q], fz[q]); st4(out.F[3] + rc.go[q], fw[q]);
+    }
   }
 }
 
-// flowApply.comp:32-52 for the lane's 8 cells.  Reads the neighbour rows' +-Y outflow; not LAST:
+// flowApply.comp:32-52 for the lane's 4*G cells.  Reads the neighbour rows' +-Y outflow; not LAST:
 // new depth stays in registers and the new water level is published; LAST: depth and the packed
 // fp16 flow vector go to HBM.
-template <bool EDGE, bool LAST>
-__device__ __forceinline__ void stream_depth(const float* __restrict__ sFypUp, const float* __restrict__ sFymDn, float* __restrict__ sH,
-                                             const int oa, const int ob, const float4 (&h)[2], float4 (&d)[2], const float4 (&fx)[2],
-                                             const float4 (&fy)[2], const float4 (&fz)[2], const float4 (&fw)[2], const RowCtx& rc,
-                                             const FusedOut& out, const Geom& g, const StepConsts& c, const int lane) {
-  float4 iy1[2], iy0[2];
-  iy1[0] = ld4(sFymDn + oa); iy1[1] = ld4(sFymDn + ob);      // F(x,y+1).w, flowApply.comp:34
-  iy0[0] = ld4(sFypUp + oa); iy0[1] = ld4(sFypUp + ob);      // F(x,y-1).z, :35
-  float l[2], r[2];
-  // F(x-1,y).x (:33) is the left cell's +X outflow, F(x+1,y).y (:32) the right cell's -X outflow
-  x_neighbours(fx[0].w, fx[1].w, fy[0].x, fy[1].x, lane, l[0], l[1], r[0], r[1]);
+template <int G, int SXW, bool EDGE, bool LAST, bool EXT>
+__device__ __forceinline__ void stream_depth(const float* __restrict__ up, const float* __restrict__ dn, float* __restrict__ me, const int lane,
+                                             const float4 (&h)[G], float4 (&d)[G], const float4 (&fx)[G], const float4 (&fy)[G],
+                                             const float4 (&fz)[G], const float4 (&fw)[G], const RowCtx<G>& rc, const FusedOut& out,
+                                             const Geom& g, const StepConsts& c) {
+  float4 iy1[G], iy0[G];
+  float w3[G], x0[G], l[G], r[G];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int gx0 = q ? rc.gxb : rc.gxa;
+  for (int q = 0; q < G; ++q) {
+    iy1[q] = ld4(dn + 2 * SXW + 128 * q);      // F(x,y+1).w, flowApply.comp:34
+    iy0[q] = ld4(up + SXW + 128 * q);          // F(x,y-1).z, :35
+    w3[q] = fx[q].w; x0[q] = fy[q].x;
+  }
+  // F(x-1,y).x (:33) is the left cell's +X outflow, F(x+1,y).y (:32) the right cell's -X outflow
+  x_neighbours<G>(w3, x0, lane, l, r);
+#pragma unroll
+  for (int q = 0; q < G; ++q) {
     float nd[4]; uint32_t nv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float iX1 = (i < 3) ? comp(fy[q], i + 1) : r[q];
       const float iX0 = (i > 0) ? comp(fx[q], i - 1) : l[q];
       float vx, vy;
-      nd[i] = apply_cell(comp(d[q], i), comp(fx[q], i), comp(fy[q], i), comp(fz[q], i), comp(fw[q], i), iX1, iX0, comp(iy1[q], i),
-                         comp(iy0[q], i), c, vx, vy);
+      nd[i] = apply_cell_t<EXT>(comp(d[q], i), comp(fx[q], i), comp(fy[q], i), comp(fz[q], i), comp(fw[q], i), iX1, iX0, comp(iy1[q], i),
+                                comp(iy0[q], i), c, vx, vy);
       if (LAST) nv[i] = pack_half2(vx, vy);
-      if (EDGE && !(rc.row_in && (unsigned)(gx0 + i) < (unsigned)g.W)) { nd[i] = 0.f; if (LAST) nv[i] = 0u; }
+      if (EDGE && !(rc.row_in && (unsigned)(rc.gx[q] + i) < (unsigned)g.W)) { nd[i] = 0.f; if (LAST) nv[i] = 0u; }
     }
     if (!LAST) {
       d[q] = make_float4(nd[0], nd[1], nd[2], nd[3]);
-      st4(sH + (q ? ob : oa), add4(d[q], h[q]));
-    } else if (rc.store && (q ? rc.stb : rc.sta)) {
-      const size_t go = q ? rc.gob : rc.goa;
-      st4(out.d + go, make_float4(nd[0], nd[1], nd[2], nd[3]));
-      *reinterpret_cast<uint4*>(out.v + go) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+      st4(me + 128 * q, add4(d[q], h[q]));
+    } else if (rc.store && rc.st[q]) {
+      st4(out.d + rc.go[q], make_float4(nd[0], nd[1], nd[2], nd[3]));
+      *reinterpret_cast<uint4*>(out.v + rc.go[q]) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
     }
   }
 }
 
-template <class C>
+template <class C, bool EXT>
 __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_constant__ CUtensorMap tm_h,
                                                                const __grid_constant__ CUtensorMap tm_d,
                                                                const __grid_constant__ CUtensorMap tm_f0,
@@ -201,26 +285,31 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
                                                                const __grid_constant__ CUtensorMap tm_f3,
                                                                FusedOut out, Geom g, StepConsts c, int lr0, int lr1, int nstrips,
                                                                int tma_y_bias) {
-  constexpr int K = C::K, NW = C::NW, SXW = C::SXW, HX = C::HX, OX = C::OX, NHP = C::NHP, LAND = C::LAND;
+  constexpr int K = C::K, NW = C::NW, G = C::G, SXW = C::SXW, HX = C::HX, OX = C::OX, NHP = C::NHP, LAND = C::LAND;
   extern __shared__ __align__(1024) float smem[];
   __shared__ uint64_t full[NW];
+  __shared__ __align__(16) uint64_t evt[NW][NHP][2];      // per slot, half-pass and ring-turn parity
   __shared__ uint32_t progress[NW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wup = (warp + NW - 1) % NW, wdn = (warp + 1) % NW;
 
-  float* land = smem + warp * LAND;                       // this warp's landing buffer
-  float* xch = smem + NW * LAND;                          // exchange slots: [NW][H | F+Y | F-Y][SXW]
-  float* sH_me = xch + warp * C::XROW;            float* sFyp_me = sH_me + SXW;            float* sFym_me = sH_me + 2 * SXW;
-  const float* sH_up = xch + wup * C::XROW;       const float* sFyp_up = sH_up + SXW;
-  const float* sH_dn = xch + wdn * C::XROW;       const float* sFym_dn = sH_dn + 2 * SXW;
-  const int oa = lane * 4, ob = 128 + lane * 4;
+  // lane-resolved pointers: landing buffer; exchange slots [NW][H | F+Y | F-Y][SXW] of this row and its neighbours
+  float* land = smem + warp * LAND;
+  const float* land_l = land + lane * 4;
+  float* xch = smem + NW * LAND + lane * 4;
+  float* x_me = xch + warp * C::XROW;
+  const float* x_up = xch + wup * C::XROW;
+  const float* x_dn = xch + wdn * C::XROW;
 
   if (tid == 0) {
 #pragma unroll 1
     for (int i = 0; i < NW; ++i) mbar_init(&full[i], 1);
+#pragma unroll 1
+    for (int i = 0; i < NW * NHP * 2; ++i) mbar_init(&evt[0][0][0] + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   uint32_t parity = 0;                                    // phase of this warp's landing barrier
+  uint32_t turn_base = 0;                                 // ring turns completed by earlier pieces (event-barrier phases)
 
   // This CTA's piece of the (strip, row) list: pieces are equal, contiguous, strip-major.
   const long long R = (long long)(lr1 - lr0);
@@ -236,6 +325,7 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
     const int sx0 = strip * OX - HX;
     const int ystart = ya - 2 * K;                        // 2K warm-up rows above, 2K feeder rows below
     const int nrows = (yb - ya) + 4 * K;
+    const int turns = (nrows + NW - 1) / NW;
     const bool xedge = sx0 < 0 || sx0 + SXW > g.W;
 
     __syncthreads();                                      // every warp is done with the previous piece
@@ -255,81 +345,116 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
     };
     if (lane == 0 && warp < nrows) issue(ystart + warp);
 
-    RowCtx rc;
-    rc.gxa = sx0 + oa; rc.gxb = sx0 + ob;
-    rc.sta = oa >= HX && oa < HX + OX && rc.gxa < g.pitch;
-    rc.stb = ob >= HX && ob < HX + OX && rc.gxb < g.pitch;
+    RowCtx<G> rc;
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      const int o = (lane + 32 * q) * 4;
+      rc.gx[q] = sx0 + o;
+      rc.st[q] = o >= HX && o < HX + OX && rc.gx[q] < g.pitch;
+    }
 
 #pragma unroll 1
-    for (int idx = warp; idx < nrows; idx += NW) {
+    for (int t = 0; t < turns; ++t) {
+      const int idx = t * NW + warp;
+      const uint32_t turn = turn_base + (uint32_t)t;
+      RowSync sy;
+#if TWS_STREAM_WAIT == 4
+      // neighbours' turns: the row above a slot-0 row lives in the previous turn, the row below a last-slot row in the next
+      const uint32_t tu = warp == 0 ? turn - 1u : turn, td = warp == NW - 1 ? turn + 1u : turn;
+      sy.up = smem_u32(&evt[wup][0][tu & 1u]); sy.pu = (tu >> 1) & 1u;
+      sy.dn = smem_u32(&evt[wdn][0][td & 1u]); sy.pd = (td >> 1) & 1u;
+      sy.me = smem_u32(&evt[warp][0][turn & 1u]);
+      sy.val = 0;
+      if (idx >= nrows) {                                 // no row for this slot in the last turn: keep the phase counts uniform
+        if (lane == 0)
+          for (int e = 0; e < NHP; ++e) mbar_arrive(sy.me + 16 * e);
+        break;
+      }
+#else
+      if (idx >= nrows) break;
+      sy.up = smem_u32(&progress[wup]); sy.dn = smem_u32(&progress[wdn]); sy.me = smem_u32(&progress[warp]);
+      sy.pu = (uint32_t)(idx - 1) * NHP + 1u; sy.pd = (uint32_t)(idx + 1) * NHP + 1u;      // neighbour has finished half-pass 0
+      sy.val = (uint32_t)idx * NHP + 1u;
+#endif
+      sy.up_on = idx > 0;
       const int y = ystart + idx;                         // local row
       rc.gy = g.row0 + y;
       rc.row_in = (unsigned)rc.gy < (unsigned)g.Hg;
       rc.store = y >= ya && y < yb;
       const size_t rowoff = (size_t)((long long)y * g.pitch);      // only dereferenced when rc.store (y >= 0)
-      rc.goa = rowoff + rc.gxa; rc.gob = rowoff + rc.gxb;
+#pragma unroll
+      for (int q = 0; q < G; ++q) rc.go[q] = rowoff + rc.gx[q];
       // rows below the piece only feed the rows above them: row yb-1+m stops after half-pass 2K-m
       const int smax = (y < yb) ? 2 * K : 2 * K - (y - yb + 1);
       const bool edge = xedge || rc.gy <= 0 || rc.gy >= g.Hg - 1;
-      const uint32_t base_me = (uint32_t)idx * NHP, base_dn = base_me + NHP;
-      const uint32_t base_up = idx > 0 ? base_me - NHP : 0u;      // the first row has nobody above: 0 is always reached
-      const uint32_t up_on = idx > 0 ? 1u : 0u;
 
       // ---- half-pass 0: registers <- landing buffer; publish H; prefetch this warp's next row ----
-      float4 h[2], d[2], fx[2], fy[2], fz[2], fw[2];
+      float4 h[G], d[G], fx[G], fy[G], fz[G], fw[G];
       mbar_wait(&full[warp], parity);
       parity ^= 1u;
-      h[0] = ld4(land + oa);            h[1] = ld4(land + ob);
-      d[0] = ld4(land + SXW + oa);      d[1] = ld4(land + SXW + ob);
-      fx[0] = ld4(land + 2 * SXW + oa); fx[1] = ld4(land + 2 * SXW + ob);
-      fy[0] = ld4(land + 3 * SXW + oa); fy[1] = ld4(land + 3 * SXW + ob);
-      fz[0] = ld4(land + 4 * SXW + oa); fz[1] = ld4(land + 4 * SXW + ob);
-      fw[0] = ld4(land + 5 * SXW + oa); fw[1] = ld4(land + 5 * SXW + ob);
+#pragma unroll
+      for (int q = 0; q < G; ++q) {
+        h[q] = ld4(land_l + 128 * q);            d[q] = ld4(land_l + SXW + 128 * q);
+        fx[q] = ld4(land_l + 2 * SXW + 128 * q); fy[q] = ld4(land_l + 3 * SXW + 128 * q);
+        fz[q] = ld4(land_l + 4 * SXW + 128 * q); fw[q] = ld4(land_l + 5 * SXW + 128 * q);
+      }
       __syncwarp();
       if (lane == 0 && idx + NW < nrows) issue(y + NW);
-      st4(sH_me + oa, add4(d[0], h[0]));
-      st4(sH_me + ob, add4(d[1], h[1]));
-      signal_row(&progress[warp], base_me + 1, lane);
+#pragma unroll
+      for (int q = 0; q < G; ++q) st4(x_me + 128 * q, add4(d[q], h[q]));
+      sy.signal(lane);
 
-      // ---- levels 1..K-1 (results stay on chip) --------------------------------------------------
-      int s = 1;
+      if (!edge && smax == 2 * K) {
+        // ---- the common row: interior, all 2K half-passes, no masks ----------------------------
 #pragma unroll 1
-      for (int t = 1; t < K && s <= smax; ++t) {
-        wait_rows(&progress[wup], (base_up + s) * up_on, &progress[wdn], base_dn + s);
-        if (edge) stream_flux<true, false>(sH_up, sH_dn, sFyp_me, sFym_me, oa, ob, h, d, fx, fy, fz, fw, rc, out, g, c, lane);
-        else stream_flux<false, false>(sH_up, sH_dn, sFyp_me, sFym_me, oa, ob, h, d, fx, fy, fz, fw, rc, out, g, c, lane);
-        signal_row(&progress[warp], base_me + s + 1, lane);
-        ++s;
-        if (s > smax) break;
-        wait_rows(&progress[wup], (base_up + s) * up_on, &progress[wdn], base_dn + s);
-        if (edge) stream_depth<true, false>(sFyp_up, sFym_dn, sH_me, oa, ob, h, d, fx, fy, fz, fw, rc, out, g, c, lane);
-        else stream_depth<false, false>(sFyp_up, sFym_dn, sH_me, oa, ob, h, d, fx, fy, fz, fw, rc, out, g, c, lane);
-        signal_row(&progress[warp], base_me + s + 1, lane);
-        ++s;
-      }
-      // ---- level K: flux and depth / velocity go to HBM straight from registers -------------------
-      if (s == 2 * K - 1 && s <= smax) {
-        wait_rows(&progress[wup], (base_up + s) * up_on, &progress[wdn], base_dn + s);
-        if (edge) stream_flux<true, true>(sH_up, sH_dn, sFyp_me, sFym_me, oa, ob, h, d, fx, fy, fz, fw, rc, out, g, c, lane);
-        else stream_flux<false, true>(sH_up, sH_dn, sFyp_me, sFym_me, oa, ob, h, d, fx, fy, fz, fw, rc, out, g, c, lane);
-        signal_row(&progress[warp], base_me + s + 1, lane);
-        ++s;
-        if (s <= smax) {
-          wait_rows(&progress[wup], (base_up + s) * up_on, &progress[wdn], base_dn + s);
-          if (edge) stream_depth<true, true>(sFyp_up, sFym_dn, sH_me, oa, ob, h, d, fx, fy, fz, fw, rc, out, g, c, lane);
-          else stream_depth<false, true>(sFyp_up, sFym_dn, sH_me, oa, ob, h, d, fx, fy, fz, fw, rc, out, g, c, lane);
-          signal_row(&progress[warp], base_me + s + 1, lane);
+        for (int lv = 1; lv < K; ++lv) {
+          sy.wait();
+          stream_flux<G, SXW, false, false>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+          sy.signal(lane);
+          sy.wait();
+          stream_depth<G, SXW, false, false, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+          sy.signal(lane);
         }
+        sy.wait();
+        stream_flux<G, SXW, false, true>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+        sy.signal(lane);
+        sy.wait();
+        stream_depth<G, SXW, false, true, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+        sy.signal(lane);
+      } else {
+        // ---- rows on the grid edge (exterior masks, boundary mode) and feeder rows that stop early ----
+        int s = 1;
+#pragma unroll 1
+        for (; s <= smax; ++s) {
+          sy.wait();
+          const bool last = s >= 2 * K - 1;
+          if (s & 1) {
+            if (last) stream_flux<G, SXW, true, true>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+            else stream_flux<G, SXW, true, false>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+          } else {
+            if (last) stream_depth<G, SXW, true, true, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+            else stream_depth<G, SXW, true, false, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+          }
+          sy.signal(lane);
+        }
+#if TWS_STREAM_WAIT == 4
+        if (lane == 0)                                    // the half-passes this feeder row skipped
+          for (; s <= 2 * K; ++s) { mbar_arrive(sy.me); sy.me += 16; }
+#endif
       }
     }
+    turn_base += (uint32_t)turns;
   }
 }
 
 // ---- host side ---------------------------------------------------------------------------
-#ifndef TWS_STREAM_NW
-#define TWS_STREAM_NW 16
+#ifndef TWS_STREAM_G
+#define TWS_STREAM_G 1           // float4 groups per lane: rows of 128 * G cells
 #endif
-template <int K> struct StreamCfgFor { using type = StreamCfg<K, TWS_STREAM_NW>; };
+#ifndef TWS_STREAM_NW
+#define TWS_STREAM_NW (24 / TWS_STREAM_G)     // row slots (warps) per SM: 24 x 80 registers keeps the row state spill-free
+#endif
+template <int K> struct StreamCfgFor { using type = StreamCfg<K, TWS_STREAM_NW, TWS_STREAM_G>; };
 
 static int stream_sm_count() {
   static int cached[64] = {};
@@ -339,14 +464,14 @@ static int stream_sm_count() {
   return cached[dev & 63] > 0 ? cached[dev & 63] : 148;
 }
 
-template <int K>
+template <int K, bool EXT>
 static cudaError_t launch_stream_k(const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
                                    cudaStream_t st) {
   using C = typename StreamCfgFor<K>::type;
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = stream_step_kernel<C>;
+  auto kern = stream_step_kernel<C, EXT>;
   if (!attr_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return e;
@@ -373,19 +498,20 @@ static cudaError_t launch_stream_k(const Geom& g, const Planes& p, const TmaSet&
 
 cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
                           cudaStream_t st) {
+  const bool ext = c.ext_sources != 0;
   switch (K) {
-    case 1: return launch_stream_k<1>(g, p, tma, src, c, lr0, lr1, st);
-    case 2: return launch_stream_k<2>(g, p, tma, src, c, lr0, lr1, st);
-    case 3: return launch_stream_k<3>(g, p, tma, src, c, lr0, lr1, st);
-    case 4: return launch_stream_k<4>(g, p, tma, src, c, lr0, lr1, st);
+    case 1: return ext ? launch_stream_k<1, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<1, false>(g, p, tma, src, c, lr0, lr1, st);
+    case 2: return ext ? launch_stream_k<2, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<2, false>(g, p, tma, src, c, lr0, lr1, st);
+    case 3: return ext ? launch_stream_k<3, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<3, false>(g, p, tma, src, c, lr0, lr1, st);
+    case 4: return ext ? launch_stream_k<4, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<4, false>(g, p, tma, src, c, lr0, lr1, st);
     default: return cudaErrorInvalidValue;
   }
 }
 
-// Row descriptors: box = one 256-cell row segment.  Same visibility rule as the tile kernel's maps
+// Row descriptors: box = one SXW-cell row segment.  Same visibility rule as the tile kernel's maps
 // (own rows plus the halo rows towards an existing neighbour; everything else zero-filled).
 cudaError_t stream_build_tma(const Geom& g, const Planes& p, int side, TmaSet* out, std::string* err) {
-  return build_tma_boxes(g, p, side, StreamCfgFor<1>::type::SXW, 1, out, err);
+  return build_tma_boxes(g, p, side, StreamCfgFor<1>::type::SXW, 1, out, err, TWS_STREAM_L2PROMO);
 }
 
 }  // namespace tws

@@ -72,7 +72,8 @@ cudaError_t fused_build_tma(int K, const Geom& g, const Planes& p, int side, Tma
 cudaError_t launch_fused(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c,
                          int ty0, int ty1, cudaStream_t st);
 // Row-streaming pipeline (stream_kernels.cu): K steps over local rows [lr0, lr1) of the strip.
-cudaError_t build_tma_boxes(const Geom& g, const Planes& p, int side, int box_x, int box_y, TmaSet* out, std::string* err);
+cudaError_t build_tma_boxes(const Geom& g, const Planes& p, int side, int box_x, int box_y, TmaSet* out, std::string* err,
+                            int l2_promotion);   // 0 none, 1 128 B, 2 256 B
 cudaError_t stream_build_tma(const Geom& g, const Planes& p, int side, TmaSet* out, std::string* err);
 cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c,
                           int lr0, int lr1, cudaStream_t st);

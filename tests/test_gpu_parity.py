@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 GOLD = json.loads((ROOT / "tests" / "golden" / "goldens.json").read_text())
 
-BACKENDS = [("unfused", 1, 1), ("fused", 2, 1), ("tb2", 3, 2), ("tb3", 3, 3), ("tb4", 3, 4)]
+BACKENDS = [("unfused", 1, 1), ("fused", 2, 1), ("tb2", 3, 2), ("tb3", 3, 3), ("tb4", 3, 4),
+            ("stream1", 4, 1), ("stream2", 4, 2), ("stream3", 4, 3), ("stream4", 4, 4)]
 
 
 def bits(a):
@@ -76,7 +77,7 @@ def test_config1_dam_break_1000_steps(tws, oracle_omp, name, backend, k, rim):
             assert abs(v1 - v0) / v0 < 1e-6          # closed domain: volume conserved to 1e-6 (north_star)
 
 
-@pytest.mark.parametrize("name,backend,k", [BACKENDS[0], BACKENDS[1], BACKENDS[4]])
+@pytest.mark.parametrize("name,backend,k", [BACKENDS[0], BACKENDS[1], BACKENDS[4], BACKENDS[6], BACKENDS[8]])
 def test_config2_reference_scene_with_brush_1000_steps(tws, oracle_omp, name, backend, k):
     """BASELINE config 2: 1024x1024 reference default scene (generated ON THE GPU), brush at
     (512,512) with intensity 100/60 before every step (Scene.cpp:356-363), 1000 steps."""
