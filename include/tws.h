@@ -177,8 +177,13 @@ tws_status tws_boundary_outflow(tws_sim* s, double* flux_sum);
  * launching stream; replaces gl::TimerQuery around PerformSimulationStep,
  * Scene.cpp:362-364).  Synchronises on the end event. */
 tws_status tws_elapsed_ms(tws_sim* s, float* ms);
-/* Number of kernels launched by this sim since creation. */
+/* Number of kernels launched by this sim since creation (kernels inside a replayed batch graph count). */
 uint64_t   tws_kernel_launches(const tws_sim* s);
+/* Frame scheduler: a whole-grid sim captures each batch size n (2..64) of tws_step / tws_advance as
+ * one CUDA graph per ping-pong side and replays it (the reference issues ~12 GL calls per step,
+ * Terrain.cpp:253-265, up to 10 steps per frame).  Returns how many batches ran as a graph replay.
+ * Environment TWS_GRAPHS=0 disables capture (every kernel launched individually). */
+uint64_t   tws_graph_replays(const tws_sim* s);
 /* Raw device pointer and row pitch (in elements) of a planar field for zero-copy
  * consumers (CUDA interop); planes: TERRAIN, WATER (current), VELOCITY. */
 tws_status tws_device_view(tws_sim* s, tws_field field, void** device_ptr, int64_t* pitch_elems);

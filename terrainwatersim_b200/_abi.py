@@ -98,6 +98,7 @@ SYMBOLS = {
     "tws_boundary_outflow": (C.c_int, [_SIM, C.POINTER(C.c_double)]),
     "tws_elapsed_ms": (C.c_int, [_SIM, C.POINTER(C.c_float)]),
     "tws_kernel_launches": (C.c_uint64, [_SIM]),
+    "tws_graph_replays": (C.c_uint64, [_SIM]),
     "tws_device_view": (C.c_int, [_SIM, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "tws_halo_export": (C.c_int, [_SIM, C.POINTER(TwsHaloHandle)]),
     "tws_halo_connect": (C.c_int, [_SIM, C.POINTER(TwsHaloHandle), C.POINTER(TwsHaloHandle)]),

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -61,6 +62,11 @@ struct tws_sim {
   size_t staging_bytes = 0;
   void* packed_info = nullptr;       // publish buffers
   void* packed_flow = nullptr;
+  // Captured step batches (frame scheduler): one executable graph per (n, ping-pong side).
+  struct StepGraph { int n; int cur; int cur_after; uint64_t launches; cudaGraphExec_t exec; };
+  std::vector<StepGraph> graphs;
+  bool use_graphs = true;
+  uint64_t graph_replays = 0;
   std::string err;
 };
 
@@ -109,7 +115,9 @@ void layout_planes(uint8_t* base, int pitch, int rows, Planes* p, size_t* plane_
 int pitch_for(int width) { return (int)align_up((size_t)width, 64); }
 
 // Terrain.cpp:175-198 — see tws_step_constants in tws.h.
+void drop_graphs(tws_sim* s);
 void derive_constants(tws_sim* s) {
+  drop_graphs(s);                                       // captured batches bake the constants in
   const tws_params& p = s->prm;
   s->step_length = (double)(1.0f / p.steps_per_second);                   // ezTime::Seconds(1.0f / sps)
   const float cell = p.world_size / (float)p.width;                       // float / uint -> float
@@ -282,12 +290,73 @@ tws_status run_block(tws_sim* s, int k) {
   return TWS_OK;
 }
 
+void drop_graphs(tws_sim* s) {
+  for (auto& e : s->graphs) cudaGraphExecDestroy(e.exec);
+  s->graphs.clear();
+}
+
+// A batch of n steps as one CUDA graph: the reference runs up to 10 steps per frame
+// (Terrain.cpp:247,253-265) with ~12 GL calls each; on small grids a step is a few microseconds of
+// GPU time and the launch path dominates, so whole-grid sims replay a captured batch instead of
+// re-launching its kernels one by one.  Captured once per (n, ping-pong side); parameter changes
+// drop the cache (the per-step constants are baked into the kernel arguments).
+tws_status run_batch_graph(tws_sim* s, int n, int K, bool* done) {
+  *done = false;
+  for (const auto& e : s->graphs)
+    if (e.n == n && e.cur == s->cur) {
+      TWS_CUDA(s, cudaGraphLaunch(e.exec, s->st_main));
+      s->cur = e.cur_after; s->launches += e.launches; s->graph_replays += 1;
+      *done = true;
+      return TWS_OK;
+    }
+  // make sure nothing but kernel launches happens inside the capture
+  if (s->prm.backend == TWS_BACKEND_STREAM_TB) {
+    tws_status r = ensure_tma_stream(s); if (r) return r;
+    for (int k : {K, n % K}) if (k > 0) TWS_CUDA(s, launch_stream(k, s->geom, s->planes, s->tma_stream[0], 0, s->consts, 0, 0, s->st_main));
+  } else if (s->prm.backend != TWS_BACKEND_UNFUSED) {
+    for (int k : {K, n % K}) if (k > 0) {
+      tws_status r = ensure_tma(s, k); if (r) return r;
+      TWS_CUDA(s, launch_fused(k, s->geom, s->planes, s->tma[k][0], 0, s->consts, 0, 0, s->st_main));
+    }
+  }
+  if (s->graphs.size() >= 16) drop_graphs(s);
+  tws_sim::StepGraph e{n, s->cur, 0, 0, nullptr};
+  const uint64_t l0 = s->launches;
+  TWS_CUDA(s, cudaStreamBeginCapture(s->st_main, cudaStreamCaptureModeThreadLocal));
+  tws_status r = TWS_OK;
+  for (int left = n; left > 0 && r == TWS_OK;) {
+    const int k = std::min(left, K);
+    r = run_block(s, k);
+    left -= k;
+  }
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(s->st_main, &graph);
+  e.cur_after = s->cur; e.launches = s->launches - l0;
+  s->cur = e.cur; s->launches = l0;                      // nothing has run yet
+  if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+  if (ce != cudaSuccess) return cuda_fail(s, ce, "cudaStreamEndCapture");
+  ce = cudaGraphInstantiate(&e.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) return cuda_fail(s, ce, "cudaGraphInstantiate");
+  s->graphs.push_back(e);
+  TWS_CUDA(s, cudaGraphLaunch(e.exec, s->st_main));
+  s->cur = e.cur_after; s->launches += e.launches; s->graph_replays += 1;
+  *done = true;
+  return TWS_OK;
+}
+
 tws_status run_steps(tws_sim* s, int n) {
   const Geom& g = s->geom;
   const bool strip = g.has_up || g.has_down;
   if (strip && !s->connected) return fail(s, TWS_ERR_STATE, "strip sim stepped before tws_halo_connect");
   TWS_CUDA(s, cudaEventRecord(s->ev_start, s->st_main));
   const int K = (s->prm.backend == TWS_BACKEND_FUSED_TB || s->prm.backend == TWS_BACKEND_STREAM_TB) ? s->K : 1;
+  if (!strip && s->use_graphs && n >= 2 && n <= 64) {
+    bool done = false;
+    tws_status r = run_batch_graph(s, n, K, &done);
+    if (r) return r;
+    if (done) n = 0;
+  }
   while (n > 0) {
     const int k = std::min(n, K);
     tws_status r = run_block(s, k);
@@ -372,6 +441,7 @@ tws_status tws_create(const tws_params* p, tws_sim** out) {
   if (!s) return fail(nullptr, TWS_ERR_NOMEM, "tws_create: out of host memory");
   s->prm = *p;
   s->K = (p->backend == TWS_BACKEND_FUSED_TB || p->backend == TWS_BACKEND_STREAM_TB) ? p->temporal_block : 1;
+  if (const char* gv = getenv("TWS_GRAPHS")) s->use_graphs = gv[0] != '0';
   DeviceGuard guard(p->device);
   Geom& g = s->geom;
   g.W = p->width; g.Hg = p->height; g.row0 = p->row_begin; g.rows = p->row_end - p->row_begin;
@@ -409,6 +479,7 @@ tws_status tws_destroy(tws_sim* s) {
   if (s->st_main) cudaStreamSynchronize(s->st_main);
   if (s->st_edge) cudaStreamSynchronize(s->st_edge);
   close_peer(s->up); close_peer(s->down);
+  drop_graphs(s);
   if (s->staging) cudaFree(s->staging);
   if (s->partials) cudaFree(s->partials);
   if (s->white_dev) cudaFree(s->white_dev);
@@ -640,6 +711,7 @@ tws_status tws_elapsed_ms(tws_sim* s, float* ms) {
 }
 
 uint64_t tws_kernel_launches(const tws_sim* s) { return s ? s->launches : 0; }
+uint64_t tws_graph_replays(const tws_sim* s) { return s ? s->graph_replays : 0; }
 
 tws_status tws_device_view(tws_sim* s, tws_field field, void** ptr, int64_t* pitch) {
   if (!s || !ptr || !pitch) return TWS_ERR_INVALID;

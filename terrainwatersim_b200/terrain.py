@@ -131,6 +131,9 @@ class Terrain:
     def kernel_launches(self) -> int:
         return int(self._lib.tws_kernel_launches(self._sim))
 
+    def graph_replays(self) -> int:
+        return int(self._lib.tws_graph_replays(self._sim))
+
     def step_constants(self) -> Tuple[float, float, float]:
         c = _abi.TwsStepConstants()
         self._check(self._lib.tws_get_step_constants(self._sim, C.byref(c)))
