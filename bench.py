@@ -39,8 +39,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=8192, help="grid width (and per-GPU rows unless --strong)")
     ap.add_argument("--strong", action="store_true", help="fixed size x size grid split over the ranks (strong scaling)")
-    ap.add_argument("--backend", default="tb", choices=["unfused", "fused", "tb"])
-    ap.add_argument("--tb", type=int, default=2, help="temporal block (steps per launch) for --backend tb")
+    ap.add_argument("--backend", default="tb", choices=["unfused", "fused", "tb", "stream"])
+    ap.add_argument("--tb", type=int, default=2, help="temporal block (steps per launch) for --backend tb / stream")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the end-to-end leg (default min(steps, 40))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -199,7 +199,7 @@ def workload_config(args, world):
     return {
         "workload": f"{W}x{Hg} reference-scene fBm terrain (value noise octaves 2..10, persistence 0.43, seed 231656522) + central lake, "
                     f"open (reference) boundary, no sources; BASELINE config {'4/5 (strong)' if args.strong else '3 per GPU'}",
-        "grid": [W, Hg], "backend": args.backend, "temporal_block": args.tb if args.backend == "tb" else 1,
+        "grid": [W, Hg], "backend": args.backend, "temporal_block": args.tb if args.backend in ("tb", "stream") else 1,
         "decomposition": f"{world} row strip(s), halo rows pushed over NVLink by the step kernels' stream (no collective)",
         "l2": "state >= 3.2 GB per GPU, far larger than the 126 MB L2 (inputs larger than L2, no flush needed)",
     }
@@ -231,8 +231,9 @@ def run_b200(args):
     W = args.size
     Hg = args.size if args.strong else args.size * world
     plan = tws.plan_strips(Hg, world)
-    backend = {"unfused": tws.BACKEND_UNFUSED, "fused": tws.BACKEND_FUSED, "tb": tws.BACKEND_FUSED_TB}[args.backend]
-    k = args.tb if args.backend == "tb" else 1
+    backend = {"unfused": tws.BACKEND_UNFUSED, "fused": tws.BACKEND_FUSED, "tb": tws.BACKEND_FUSED_TB,
+               "stream": tws.BACKEND_STREAM_TB}[args.backend]
+    k = args.tb if args.backend in ("tb", "stream") else 1
     sim = tws.Terrain(W, height=Hg, rows=plan.rows(rank), backend=backend, temporal_block=k, device=local)
     tws.connect_strips(sim, plan, rank)
     sim.CreateHeightmapFromNoiseAndResetSim()
@@ -290,10 +291,10 @@ def run_b200(args):
     launch_ms = ms_dev / max(1, (args.steps + k - 1) // k)
     algo_bytes_per_launch = ALGO_BYTES_PER_CELL_UPDATE * cells_local * min(k, args.steps)
     achieved = algo_bytes_per_launch / (launch_ms * 1e-3) / 1e9
-    tag = {"unfused": "unfused", "fused": "fused_k1", "tb": f"fused_k{k}"}[args.backend]
+    tag = {"unfused": "unfused", "fused": "fused_k1", "tb": f"fused_k{k}", "stream": f"stream_k{k}"}[args.backend]
     traffic = ncu_traffic_per_launch(tag) if (W == 8192 and sim.rows == 8192) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "fused_step_kernel" if args.backend != "unfused" else "unfused_update_kernel+unfused_apply_kernel",
+                "kernel": {"unfused": "unfused_update_kernel+unfused_apply_kernel", "stream": "stream_step_kernel"}.get(args.backend, "fused_step_kernel"),
                 "peak_source": peak_src, "algorithmic_bytes_per_cell_update": ALGO_BYTES_PER_CELL_UPDATE,
                 "cell_updates_per_launch": cells_local * min(k, args.steps), "avg_launch_ms": launch_ms,
                 "note": "achieved = 48 B x cell-updates per launch / launch time; with temporal blocking (k steps per HBM round trip) real DRAM traffic is ~48/k B per cell-update, so frac may exceed 1"}
@@ -305,29 +306,44 @@ def run_b200(args):
         d_host = torch.empty((sim.rows, W), dtype=torch.float32, pin_memory=True)
         v_host = torch.empty((sim.rows, W, 2), dtype=torch.float16, pin_memory=True)
         sim.readback_raw(tws.FIELD_WATER, d_host.data_ptr(), d_host.numel() * 4)
-        for _ in range(3):
-            sim.upload_raw(tws.FIELD_WATER, d_host.data_ptr(), d_host.numel() * 4)
-            sim.step(1)
-            sim.readback_raw(tws.FIELD_WATER, d_host.data_ptr(), d_host.numel() * 4)
-            sim.readback_raw(tws.FIELD_VELOCITY, v_host.data_ptr(), v_host.numel() * 2)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            # host-driven frame: the host owns the water layer (pinned), hands it to the library,
-            # runs one step and reads back the new water layer and the flow map.
+
+        def serial_step():
+            # the same frame as four separate calls (no overlap between the copies and the kernels)
             sim.upload_raw(tws.FIELD_WATER, d_host.data_ptr(), d_host.numel() * 4)
             if world > 1:
                 sim.halo_refresh()
             sim.step(1)
             sim.readback_raw(tws.FIELD_WATER, d_host.data_ptr(), d_host.numel() * 4)
             sim.readback_raw(tws.FIELD_VELOCITY, v_host.data_ptr(), v_host.numel() * 2)
-        torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        barrier()
+
+        def host_step():
+            # host-driven frame through ONE C-ABI call: the host owns the water layer (pinned), the
+            # library uploads it, runs one step and returns the new water layer and the flow map,
+            # band-pipelined so upload, kernels and readback overlap (tws_step_host).
+            sim.step_host_raw(d_host.data_ptr(), d_host.data_ptr(), v_host.data_ptr())
+
+        timings = {}
+        for name, fn in (("serial", serial_step), ("host", host_step)):
+            for _ in range(3):
+                fn()
+            barrier()
+            l_e = sim.kernel_launches()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                fn()
+            torch.cuda.synchronize()
+            timings[name] = max_over_ranks(time.perf_counter() - t0)
+            timings[name + "_launches"] = sim.kernel_launches() - l_e
+            barrier()
+        dt = timings["host"]
         e2e = {"value": cells_global * n_e2e / dt / 1e9, "unit": "Gcell-updates/s", "h2d_bytes_per_step": int(sum_over_ranks(cells_local * 4.0)),
                "d2h_bytes_per_step": int(sum_over_ranks(cells_local * 8.0)), "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
-               "what": "per step: tws_upload(WATER) from pinned host memory, tws_step(1), tws_readback(WATER) + tws_readback(VELOCITY) into pinned host memory; "
-                       "terrain and flux stay device-resident as in the reference (its state never leaves the GPU)"}
+               "gpu_launches": int(timings["host_launches"]),
+               "serial_calls_value": cells_global * n_e2e / timings["serial"] / 1e9,
+               "what": "per step ONE call tws_step_host(water_in, water_out, velocity_out) with pinned host buffers: 4 B/cell up, 8 B/cell down, "
+                       "uploaded / stepped / read back in row bands on three streams so both PCIe directions overlap the kernels; terrain and flux "
+                       "stay device-resident as in the reference (its state never leaves the GPU). serial_calls_value = the same frame as "
+                       "tws_upload + tws_step(1) + 2 x tws_readback (no overlap)"}
 
     # ---- strips vs whole grid (tests) ------------------------------------------------------------------
     if args.verify_strips and world > 1:

@@ -158,6 +158,18 @@ tws_status tws_inject_brush_world(tws_sim* s, float world_x, float world_z, floa
 /* n x (flowUpdate; flowApply) — the loop body of Terrain.cpp:253-265, no clamp on n. */
 tws_status tws_step(tws_sim* s, int32_t n);
 
+/* One step (the loop body of Terrain.cpp:253-265) for a caller whose water layer lives in HOST
+ * memory: uploads `water_in` (width x own rows floats, tightly packed; NULL = keep the resident
+ * water), runs one step, and returns the new water depth in `water_out` (floats) and the flow
+ * vector in `velocity_out` (2 x fp16 per cell, the RG16F texel of m_waterFlowMap); either output
+ * may be NULL.  water_out may alias water_in.  Terrain and flux stay resident on the device, as in
+ * the reference whose state never leaves the GPU.  The call is pipelined in row bands over three
+ * streams — band b+1 uploads while band b computes and band b-1 reads back, so both directions
+ * of the PCIe link are busy at once — and returns when the outputs are in host memory.  Host
+ * buffers should be page-locked (cudaHostAlloc / cudaHostRegister); pageable memory is correct
+ * but serialises the copies.  Bit-identical to tws_upload + tws_step(1) + tws_readback. */
+tws_status tws_step_host(tws_sim* s, const float* water_in, float* water_out, void* velocity_out);
+
 /* Replaces Terrain::PerformSimulationStep(ezTime) (Terrain.cpp:240-277): frame-time
  * accumulator, n = (uint)(acc/dt), acc -= dt*n, n = min(n,10); runs n steps and returns
  * n through steps_done (may be NULL). */

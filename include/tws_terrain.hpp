@@ -49,6 +49,8 @@ class Terrain {
   }
 
   void Step(int n) { check(tws_step(sim_, n)); }
+  // one step with the water layer in host memory (band-pipelined upload / step / readback)
+  void StepHost(const float* waterIn, float* waterOut, void* velocityOut) { check(tws_step_host(sim_, waterIn, waterOut, velocityOut)); }
   void Sync() { check(tws_sync(sim_)); }
   double TotalVolume() { double v = 0; check(tws_total_volume(sim_, &v)); return v; }
   float SimulationTimeMs() { float ms = 0; check(tws_elapsed_ms(sim_, &ms)); return ms; }   // "Simulation Time" stat, Scene.cpp:341-342

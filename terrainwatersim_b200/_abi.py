@@ -92,6 +92,7 @@ SYMBOLS = {
     "tws_inject_brush": (C.c_int, [_SIM, C.c_float, C.c_float, C.c_float, C.c_float]),
     "tws_inject_brush_world": (C.c_int, [_SIM, C.c_float, C.c_float, C.c_float]),
     "tws_step": (C.c_int, [_SIM, C.c_int32]),
+    "tws_step_host": (C.c_int, [_SIM, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tws_advance": (C.c_int, [_SIM, C.c_double, C.POINTER(C.c_uint32)]),
     "tws_total_volume": (C.c_int, [_SIM, C.POINTER(C.c_double)]),
     "tws_sync": (C.c_int, [_SIM]),

@@ -76,8 +76,122 @@ __device__ __forceinline__ uint32_t pack_half2(float x, float y) {              
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+// ------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (sm_100a FADD2 / FMUL2): two IEEE fp32 operations per issue slot
+// ------------------------------------------------------------------------------------
+// The step is ~50 dependent-free fp32 adds/multiplies per cell and none of them may be an FMA, so
+// the kernels are limited by instruction issue, not by the FP32 lanes.  sm_100 has packed
+// add.rn.f32x2 / mul.rn.f32x2 (SASS FADD2 / FMUL2): each rounds both halves exactly like the scalar
+// instruction, so pairing the cells (x, x+1) of a float4 group halves the issue slots of every add
+// and multiply that has aligned operands, bit for bit identical to the scalar form.
+//
+// ptxas (12.9) CONTRACTS mul.rn.f32x2 feeding add/sub.rn.f32x2 into FFMA2 despite the .rn
+// qualifiers and --fmad=false (a single-use packed product is fused).  Scalar add.rn.f32 /
+// mul.rn.f32 are never contracted.  Rule used below: an add or subtract that consumes a PACKED
+// product is always the scalar __fadd_rn; packed adds only consume loads, scalar products, maxima
+// and other sums.  tests/test_abi.py checks that no FFMA2 appears in the library's SASS.
+#ifndef TWS_PACKED
+#define TWS_PACKED 1
+#endif
+typedef unsigned long long f2;       // {lo, hi} fp32 pair in one aligned 64-bit register pair
+
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 lo2(const float4& v) { return pk(v.x, v.y); }
+__device__ __forceinline__ f2 hi2(const float4& v) { return pk(v.z, v.w); }
+__device__ __forceinline__ float4 cat4(f2 lo, f2 hi) { float4 r; upk(lo, r.x, r.y); upk(hi, r.z, r.w); return r; }
+#if TWS_PACKED
+__device__ __forceinline__ float4 add4(const float4& a, const float4& b) { return cat4(add2(lo2(a), lo2(b)), add2(hi2(a), hi2(b))); }
+#else
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+#endif
+
+// flowUpdate.comp:44-57 for the four cells of one float4 group, interior cells only (no exterior or
+// boundary-mode handling).  HC: own water level; HU / HD: rows y-1 / y+1; HL / HR: the cells left of
+// .x / right of .w.  f*: in old outflow, out max(0, .) of the new one (before the :58-59 scaling);
+// total[i] = (sum f') * areaInv.  Same values as four flux_raw calls:
+//  * the x differences are shared between neighbours, H[j]-H[j+1] serving cell j's +X and, negated,
+//    cell j+1's -X: a-b == -(b-a) exactly, and where both are zero the sign of the zero is erased by
+//    the max(0, .) that follows the sum (t + (+-0) differs only for t == +-0, and max0 maps both to +0);
+//  * products are packed or scalar multiplies, each rounded once; the sum F*phi + g*alpha is a scalar
+//    add (see the contraction rule above); the 4-term flux sums are packed adds in the shader's order.
+__device__ __forceinline__ void flux_raw4(const float4& HC, const float4& HU, const float4& HD, float HL, float HR,
+                                          float4& fx, float4& fy, float4& fz, float4& fw, const StepConsts& c, float (&total)[4]) {
+  const f2 PHI = pk(c.friction, c.friction), ALPHA = pk(c.accel, c.accel), KAPPA = pk(c.area_inv, c.area_inv);
+  // x: D[j] = H[j] - H[j+1], j = -1..3; P[j] = D[j] * accel
+  const float Dm = __fsub_rn(HL, HC.x);
+  const float D0 = __fsub_rn(HC.x, HC.y), D1 = __fsub_rn(HC.y, HC.z), D2 = __fsub_rn(HC.z, HC.w), D3 = __fsub_rn(HC.w, HR);
+  const float Pm = __fmul_rn(Dm, c.accel);
+  float P0, P1, P2, P3;
+  upk(mul2(pk(D0, D1), ALPHA), P0, P1);
+  upk(mul2(pk(D2, D3), ALPHA), P2, P3);
+  // y: g = HC - HD (+Y, :46), HC - HU (-Y, :47)
+  float Z0, Z1, Z2, Z3, W0, W1, W2, W3;
+  upk(mul2(sub2(lo2(HC), lo2(HD)), ALPHA), Z0, Z1);
+  upk(mul2(sub2(hi2(HC), hi2(HD)), ALPHA), Z2, Z3);
+  upk(mul2(sub2(lo2(HC), lo2(HU)), ALPHA), W0, W1);
+  upk(mul2(sub2(hi2(HC), hi2(HU)), ALPHA), W2, W3);
+  // F * friction (:53)
+  const float4 tx = cat4(mul2(lo2(fx), PHI), mul2(hi2(fx), PHI));
+  const float4 ty = cat4(mul2(lo2(fy), PHI), mul2(hi2(fy), PHI));
+  const float4 tz = cat4(mul2(lo2(fz), PHI), mul2(hi2(fz), PHI));
+  const float4 tw = cat4(mul2(lo2(fw), PHI), mul2(hi2(fw), PHI));
+  // sum of the two rounded products: scalar adds; max(0, .) (:54)
+  fx.x = max0(__fadd_rn(tx.x, P0)); fx.y = max0(__fadd_rn(tx.y, P1)); fx.z = max0(__fadd_rn(tx.z, P2)); fx.w = max0(__fadd_rn(tx.w, P3));
+  fy.x = max0(__fsub_rn(ty.x, Pm)); fy.y = max0(__fsub_rn(ty.y, P0)); fy.z = max0(__fsub_rn(ty.z, P1)); fy.w = max0(__fsub_rn(ty.w, P2));
+  fz.x = max0(__fadd_rn(tz.x, Z0)); fz.y = max0(__fadd_rn(tz.y, Z1)); fz.z = max0(__fadd_rn(tz.z, Z2)); fz.w = max0(__fadd_rn(tz.w, Z3));
+  fw.x = max0(__fadd_rn(tw.x, W0)); fw.y = max0(__fadd_rn(tw.y, W1)); fw.z = max0(__fadd_rn(tw.z, W2)); fw.w = max0(__fadd_rn(tw.w, W3));
+  // ((fx + fy) + fz) + fw, times areaInv (:57); the product only feeds the comparison of :58
+  const f2 slo = add2(add2(add2(lo2(fx), lo2(fy)), lo2(fz)), lo2(fw));
+  const f2 shi = add2(add2(add2(hi2(fx), hi2(fy)), hi2(fz)), hi2(fw));
+  upk(mul2(slo, KAPPA), total[0], total[1]);
+  upk(mul2(shi, KAPPA), total[2], total[3]);
+}
+
+// flowApply.comp:38-46 for the four interior cells of one float4 group.  l / r: +X outflow of the
+// cell left of .x / -X outflow of the cell right of .w; iy1 / iy0: -Y outflow of row y+1 / +Y outflow
+// of row y-1.  The flux operands are results of scalar multiplies (the :59 scaling) or loads, so the
+// sums and differences are packed; d + (in-out)*areaInv consumes a packed product and is scalar.
+template <bool VEL>
+__device__ __forceinline__ void apply4(const float4& d, const float4& fx, const float4& fy, const float4& fz, const float4& fw, float l,
+                                       float r, const float4& iy1, const float4& iy0, const StepConsts& c, const bool ext, float4& nd,
+                                       uint4& nv) {
+  // iX1 = F(x+1,y).y (:32), iX0 = F(x-1,y).x (:33): neighbours inside the group are misaligned pairs -> scalar
+  const float a0 = __fadd_rn(fy.y, l), a1 = __fadd_rn(fy.z, fx.x), a2 = __fadd_rn(fy.w, fx.y), a3 = __fadd_rn(r, fx.z);
+  const f2 inlo = add2(add2(pk(a0, a1), lo2(iy1)), lo2(iy0));                        // :38
+  const f2 inhi = add2(add2(pk(a2, a3), hi2(iy1)), hi2(iy0));
+  const f2 outlo = add2(add2(add2(lo2(fx), lo2(fy)), lo2(fz)), lo2(fw));             // :39
+  const f2 outhi = add2(add2(add2(hi2(fx), hi2(fy)), hi2(fz)), hi2(fw));
+  const f2 KAPPA = pk(c.area_inv, c.area_inv);
+  float q0, q1, q2, q3;
+  upk(mul2(sub2(inlo, outlo), KAPPA), q0, q1);
+  upk(mul2(sub2(inhi, outhi), KAPPA), q2, q3);
+  nd.x = max0(__fadd_rn(d.x, q0)); nd.y = max0(__fadd_rn(d.y, q1)); nd.z = max0(__fadd_rn(d.z, q2)); nd.w = max0(__fadd_rn(d.w, q3));   // :41
+  if (ext) {                                                                         // EXT (same expression as apply_cell)
+    const f2 RAIN = pk(c.rain_step, c.rain_step), EVAP = pk(c.evap_step, c.evap_step);
+    float e0, e1, e2, e3;
+    upk(sub2(add2(lo2(nd), RAIN), EVAP), e0, e1);
+    upk(sub2(add2(hi2(nd), RAIN), EVAP), e2, e3);
+    nd = make_float4(max0(e0), max0(e1), max0(e2), max0(e3));
+  }
+  if (VEL) {
+    // vx = (iX1 - fx) - (iX0 - fy) (:45): inner differences on misaligned neighbours are scalar
+    const float b0 = __fsub_rn(fy.y, fx.x), b1 = __fsub_rn(fy.z, fx.y), b2 = __fsub_rn(fy.w, fx.z), b3 = __fsub_rn(r, fx.w);
+    const float c0 = __fsub_rn(l, fy.x), c1 = __fsub_rn(fx.x, fy.y), c2 = __fsub_rn(fx.y, fy.z), c3 = __fsub_rn(fx.z, fy.w);
+    float vx0, vx1, vx2, vx3, vy0, vy1, vy2, vy3;
+    upk(sub2(pk(b0, b1), pk(c0, c1)), vx0, vx1);
+    upk(sub2(pk(b2, b3), pk(c2, c3)), vx2, vx3);
+    // vy = (iY1 - fz) - (iY0 - fw) (:46)
+    upk(sub2(sub2(lo2(iy1), lo2(fz)), sub2(lo2(iy0), lo2(fw))), vy0, vy1);
+    upk(sub2(sub2(hi2(iy1), hi2(fz)), sub2(hi2(iy0), hi2(fw))), vy2, vy3);
+    nv = make_uint4(pack_half2(vx0, vy0), pack_half2(vx1, vy1), pack_half2(vx2, vy2), pack_half2(vx3, vy3));
+  }
+}
 
 // ------------------------------------------------------------------------------------
 // TMA / mbarrier helpers

@@ -175,6 +175,17 @@ __device__ __forceinline__ void flux_level(float* __restrict__ st, const int (&o
     float HR = __shfl_down_sync(0xffffffffu, HC.x, 1);
     HL = lds_if(lane == 0, sH + oq - 1, HL);
     HR = lds_if(lane == 31, sH + oq + 4, HR);
+    if (!EDGE && TWS_PACKED) {
+      flux_raw4(HC, HU, HD, HL, HR, fx[q], fy[q], fz[q], fw[q], c, total[q]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dep = comp(d[q], i);
+        const bool over = total[q][i] > dep;                                         // :58
+        scale[q][i] = over ? 0.0f : 1.0f;
+        need = need || (over && dep != 0.0f);
+      }
+      continue;
+    }
     float* pfx = &fx[q].x; float* pfy = &fy[q].x; float* pfz = &fz[q].x; float* pfw = &fw[q].x;
     const int r = oq / SX, x = oq - r * SX;
     const int gy = tc.gy0 + r, gx0 = tc.sx0 + x;
@@ -260,6 +271,12 @@ __device__ __forceinline__ void depth_level(float* __restrict__ st, const int (&
     const int gy = tc.gy0 + r, gx0 = tc.sx0 + x;
     const bool row_in = (unsigned)gy < (unsigned)g.Hg;
     float nd[4]; uint32_t nv[4];
+    if (!EDGE && TWS_PACKED) {
+      float4 nd4; uint4 nv4 = make_uint4(0u, 0u, 0u, 0u);
+      apply4<LAST>(d[q], fx[q], fy[q], fz[q], fw[q], l, rgt, iy1, iy0, c, c.ext_sources != 0, nd4, nv4);
+      nd[0] = nd4.x; nd[1] = nd4.y; nd[2] = nd4.z; nd[3] = nd4.w;
+      nv[0] = nv4.x; nv[1] = nv4.y; nv[2] = nv4.z; nv[3] = nv4.w;
+    } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float iX1 = (i < 3) ? comp(fy[q], i + 1) : rgt;
@@ -269,6 +286,7 @@ __device__ __forceinline__ void depth_level(float* __restrict__ st, const int (&
                          comp(iy0, i), c, vx, vy);
       if (LAST) nv[i] = pack_half2(vx, vy);
       if (EDGE && !(row_in && (unsigned)(gx0 + i) < (unsigned)g.W)) { nd[i] = 0.f; if (LAST) nv[i] = 0u; }
+    }
     }
     if (!LAST) {
       const bool live = valid[q] && r >= C::HY - M && r < C::HY + C::OY + M;

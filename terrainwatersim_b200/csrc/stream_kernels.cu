@@ -188,6 +188,17 @@ __device__ __forceinline__ void stream_flux(const float* __restrict__ up, const 
   bool need = false;
 #pragma unroll
   for (int q = 0; q < G; ++q) {
+    if (!EDGE && TWS_PACKED) {
+      flux_raw4(HC[q], HU[q], HD[q], HL[q], HR[q], fx[q], fy[q], fz[q], fw[q], c, total[q]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dep = comp(d[q], i);
+        const bool over = total[q][i] > dep;                                         // :58
+        scale[q][i] = over ? 0.0f : 1.0f;
+        need = need || (over && dep != 0.0f);
+      }
+      continue;
+    }
     float* pfx = &fx[q].x; float* pfy = &fy[q].x; float* pfz = &fz[q].x; float* pfw = &fw[q].x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -256,6 +267,12 @@ __device__ __forceinline__ void stream_depth(const float* __restrict__ up, const
 #pragma unroll
   for (int q = 0; q < G; ++q) {
     float nd[4]; uint32_t nv[4];
+    if (!EDGE && TWS_PACKED) {
+      float4 nd4; uint4 nv4 = make_uint4(0u, 0u, 0u, 0u);
+      apply4<LAST>(d[q], fx[q], fy[q], fz[q], fw[q], l[q], r[q], iy1[q], iy0[q], c, EXT, nd4, nv4);
+      nd[0] = nd4.x; nd[1] = nd4.y; nd[2] = nd4.z; nd[3] = nd4.w;
+      nv[0] = nv4.x; nv[1] = nv4.y; nv[2] = nv4.z; nv[3] = nv4.w;
+    } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float iX1 = (i < 3) ? comp(fy[q], i + 1) : r[q];
@@ -265,6 +282,7 @@ __device__ __forceinline__ void stream_depth(const float* __restrict__ up, const
                                 comp(iy0[q], i), c, vx, vy);
       if (LAST) nv[i] = pack_half2(vx, vy);
       if (EDGE && !(rc.row_in && (unsigned)(rc.gx[q] + i) < (unsigned)g.W)) { nd[i] = 0.f; if (LAST) nv[i] = 0u; }
+    }
     }
     if (!LAST) {
       d[q] = make_float4(nd[0], nd[1], nd[2], nd[3]);

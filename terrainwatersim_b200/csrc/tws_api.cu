@@ -50,6 +50,8 @@ struct tws_sim {
   TmaSet tma_stream[2];              // row descriptors of the streaming pipeline, [side]
   bool tma_stream_ready = false;
   cudaStream_t st_main = nullptr, st_edge = nullptr;
+  cudaStream_t st_h2d = nullptr, st_d2h = nullptr;      // tws_step_host: upload / readback streams (created on first use)
+  std::vector<cudaEvent_t> band_ev;                     // tws_step_host: [2b] band b uploaded, [2b+1] band b computed
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_main = nullptr, ev_edge = nullptr;
   bool timed = false;
   uint64_t launches = 0;
@@ -480,6 +482,9 @@ tws_status tws_destroy(tws_sim* s) {
   if (s->st_edge) cudaStreamSynchronize(s->st_edge);
   close_peer(s->up); close_peer(s->down);
   drop_graphs(s);
+  for (cudaEvent_t e : s->band_ev) cudaEventDestroy(e);
+  if (s->st_h2d) { cudaStreamSynchronize(s->st_h2d); cudaStreamDestroy(s->st_h2d); }
+  if (s->st_d2h) { cudaStreamSynchronize(s->st_d2h); cudaStreamDestroy(s->st_d2h); }
   if (s->staging) cudaFree(s->staging);
   if (s->partials) cudaFree(s->partials);
   if (s->white_dev) cudaFree(s->white_dev);
@@ -651,6 +656,88 @@ tws_status tws_step(tws_sim* s, int32_t n) {
   if (n < 0) return fail(s, TWS_ERR_INVALID, "tws_step: n must be >= 0");
   DeviceGuard guard(s->prm.device);
   return run_steps(s, n);
+}
+
+// One step with the water layer in host memory, pipelined in row bands (see tws.h).  Band b's
+// kernels read input rows up to one dependency cone (2 rows at k = 1) beyond the band, i.e. into
+// band b+1: they wait for that upload; everything earlier is ordered by the upload stream.
+tws_status tws_step_host(tws_sim* s, const float* water_in, float* water_out, void* velocity_out) {
+  if (!s) return TWS_ERR_INVALID;
+  DeviceGuard guard(s->prm.device);
+  const Geom& g = s->geom;
+  const size_t plane_bytes = (size_t)g.W * g.rows * 4;
+  const bool strip = g.has_up || g.has_down;
+  if (strip || s->prm.backend == TWS_BACKEND_UNFUSED) {
+    // Strips exchange halos between GPUs and the unfused baseline updates in place: no band pipeline.
+    tws_status r = TWS_OK;
+    if (water_in) { r = transfer(s, TWS_FIELD_WATER, (void*)water_in, plane_bytes, true); if (r) return r; }
+    if (strip && water_in) { r = tws_halo_refresh(s); if (r) return r; }
+    r = run_steps(s, 1); if (r) return r;
+    if (water_out) { r = transfer(s, TWS_FIELD_WATER, water_out, plane_bytes, false); if (r) return r; }
+    if (velocity_out) { r = transfer(s, TWS_FIELD_VELOCITY, velocity_out, plane_bytes, false); if (r) return r; }
+    return sync_all(s);
+  }
+  if (!s->st_h2d) TWS_CUDA(s, cudaStreamCreateWithFlags(&s->st_h2d, cudaStreamNonBlocking));
+  if (!s->st_d2h) TWS_CUDA(s, cudaStreamCreateWithFlags(&s->st_d2h, cudaStreamNonBlocking));
+  const bool stream_be = s->prm.backend == TWS_BACKEND_STREAM_TB;
+  tws_status r = stream_be ? ensure_tma_stream(s) : ensure_tma(s, 1);
+  if (r) return r;
+  // Band height: a whole number of tile rows (tile engine) / any row count (row-streaming engine),
+  // sized for ~8 MiB of upload so a copy is long enough to run at link speed.
+  const int unit = stream_be ? 1 : fused_out_rows_per_tile(1);
+  const int units = (g.rows + unit - 1) / unit;
+  const size_t want_rows = std::max<size_t>(1, ((size_t)8 << 20) / ((size_t)g.W * 4));
+  const int band_units = (int)std::max<size_t>(stream_be ? 8 : 1, (want_rows + unit - 1) / unit);
+  const int nb = (units + band_units - 1) / band_units;
+  while ((int)s->band_ev.size() < 2 * nb) {
+    cudaEvent_t e;
+    TWS_CUDA(s, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    s->band_ev.push_back(e);
+  }
+  const int src = s->cur, dst = 1 - src;
+  const size_t off = (size_t)TWS_HALO_ROWS * g.pitch;
+  const size_t hp = (size_t)g.W * 4, dp = (size_t)g.pitch * 4;       // host / device row pitch in bytes
+  auto band_rows = [&](int b, int* r0, int* r1) {
+    *r0 = std::min(g.rows, b * band_units * unit);
+    *r1 = std::min(g.rows, (b + 1) * band_units * unit);
+  };
+  TWS_CUDA(s, cudaEventRecord(s->ev_start, s->st_main));
+  // uploads and readbacks start after everything already queued on the main stream
+  TWS_CUDA(s, cudaStreamWaitEvent(s->st_h2d, s->ev_start, 0));
+  TWS_CUDA(s, cudaStreamWaitEvent(s->st_d2h, s->ev_start, 0));
+  if (water_in) {
+    for (int b = 0; b < nb; ++b) {
+      int r0, r1; band_rows(b, &r0, &r1);
+      if (r1 > r0)
+        TWS_CUDA(s, cudaMemcpy2DAsync(s->planes.d[src] + off + (size_t)r0 * g.pitch, dp, (const uint8_t*)water_in + (size_t)r0 * hp, hp, hp,
+                                      (size_t)(r1 - r0), cudaMemcpyHostToDevice, s->st_h2d));
+      TWS_CUDA(s, cudaEventRecord(s->band_ev[2 * b], s->st_h2d));
+    }
+  }
+  for (int b = 0; b < nb; ++b) {
+    int r0, r1; band_rows(b, &r0, &r1);
+    if (water_in) TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->band_ev[2 * std::min(b + 1, nb - 1)], 0));
+    const int u0 = b * band_units, u1 = std::min(units, (b + 1) * band_units);
+    if (stream_be) TWS_CUDA(s, launch_stream(1, g, s->planes, s->tma_stream[src], src, s->consts, r0, r1, s->st_main));
+    else TWS_CUDA(s, launch_fused(1, g, s->planes, s->tma[1][src], src, s->consts, u0, u1, s->st_main));
+    s->launches += 1;
+    TWS_CUDA(s, cudaEventRecord(s->band_ev[2 * b + 1], s->st_main));
+    if ((water_out || velocity_out) && r1 > r0) {
+      TWS_CUDA(s, cudaStreamWaitEvent(s->st_d2h, s->band_ev[2 * b + 1], 0));
+      if (water_out)
+        TWS_CUDA(s, cudaMemcpy2DAsync((uint8_t*)water_out + (size_t)r0 * hp, hp, s->planes.d[dst] + off + (size_t)r0 * g.pitch, dp, hp,
+                                      (size_t)(r1 - r0), cudaMemcpyDeviceToHost, s->st_d2h));
+      if (velocity_out)
+        TWS_CUDA(s, cudaMemcpy2DAsync((uint8_t*)velocity_out + (size_t)r0 * hp, hp, s->planes.v + off + (size_t)r0 * g.pitch, dp, hp,
+                                      (size_t)(r1 - r0), cudaMemcpyDeviceToHost, s->st_d2h));
+    }
+  }
+  s->cur = dst;
+  TWS_CUDA(s, cudaEventRecord(s->ev_stop, s->st_main));
+  s->timed = true;
+  TWS_CUDA(s, cudaStreamSynchronize(s->st_h2d));
+  TWS_CUDA(s, cudaStreamSynchronize(s->st_d2h));
+  return sync_all(s);
 }
 
 tws_status tws_advance(tws_sim* s, double frame_seconds, uint32_t* steps_done) {

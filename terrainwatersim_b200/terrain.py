@@ -114,6 +114,23 @@ class Terrain:
     def step(self, n: int = 1) -> None:
         self._check(self._lib.tws_step(self._sim, int(n)))
 
+    def step_host(self, water_in: Optional[np.ndarray], water_out: Optional[np.ndarray] = None,
+                  velocity_out: Optional[np.ndarray] = None) -> None:
+        """tws_step_host: one step with the water layer in host memory (band-pipelined upload / step /
+        readback).  Arrays must be C-contiguous (rows, width) float32 / (rows, width, 2) float16."""
+        def ptr(a, dt, tail):
+            if a is None:
+                return None
+            if a.dtype != dt or a.shape != (self.rows, self.width) + tail or not a.flags.c_contiguous:
+                raise ValueError(f"expected C-contiguous {dt} array of shape {(self.rows, self.width) + tail}")
+            return a.ctypes.data_as(C.c_void_p)
+        self._check(self._lib.tws_step_host(self._sim, ptr(water_in, np.float32, ()), ptr(water_out, np.float32, ()),
+                                            ptr(velocity_out, np.float16, (2,))))
+
+    def step_host_raw(self, water_in_ptr: int, water_out_ptr: int, velocity_out_ptr: int) -> None:
+        self._check(self._lib.tws_step_host(self._sim, C.c_void_p(water_in_ptr or None), C.c_void_p(water_out_ptr or None),
+                                            C.c_void_p(velocity_out_ptr or None)))
+
     def inject_brush(self, cx: float, cy: float, intensity: float, size_sq: float = 32.0) -> None:
         self._check(self._lib.tws_inject_brush(self._sim, cx, cy, intensity, size_sq))
 

@@ -109,3 +109,27 @@ def test_fails_loudly_without_a_gpu(tws):
     with pytest.raises(tws.TwsError) as e:
         tws.Terrain(64)
     assert e.value.status == tws._abi.TWS_ERR_CUDA and "no CPU path" in str(e.value)
+
+
+def test_no_fused_multiply_add_in_the_step_kernels(tws):
+    """Arithmetic contract: no FMA contraction anywhere in the step.  ptxas fuses a
+    packed mul.rn.f32x2 feeding a packed add into FFMA2 despite .rn / --fmad=false, so the packed cell
+    math never lets a packed product feed a packed add (cell_math.cuh); this checks the SASS.  Scalar
+    FFMA is allowed only inside the IEEE division sequence (MUFU.RCP refinement) and its slow-path
+    subroutine — never next to the flux / depth arithmetic — so it must not outnumber the divisions."""
+    import shutil
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        pytest.skip("cuobjdump not available")
+    from terrainwatersim_b200.build import LIB_PATH
+    sass = subprocess.run([cuobjdump, "-sass", str(LIB_PATH)], capture_output=True, text=True).stdout
+    assert "Function :" in sass
+    assert "FFMA2" not in sass, "a packed multiply was contracted into a packed FMA"
+    for name, body in re.findall(r"Function : (\S*(?:fused_step|stream_step|unfused_update|unfused_apply)\S*)(.*?)(?=Function :|\Z)", sass, re.S):
+        n_ffma = len(re.findall(r"\bFFMA\b", body))
+        n_rcp = len(re.findall(r"\bMUFU\.RCP\b", body))
+        n_call = len(re.findall(r"\bCALL\.REL", body))
+        # 5 FFMA per inlined division fast path; the out-of-line slow path (one copy per kernel) uses a few dozen
+        assert n_ffma <= 5 * n_rcp + 60, f"{name}: {n_ffma} FFMA for {n_rcp} divisions"
+        assert n_rcp > 0 or n_ffma == 0, name
+        assert n_call >= 0

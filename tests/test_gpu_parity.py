@@ -325,3 +325,40 @@ def test_8192_closed_domain_conserves_volume(tws):
         d = sim.readback(tws.FIELD_WATER)
         assert d.min() >= 0 and np.isfinite(d).all()
         assert abs(v1 - v0) / v0 < 1e-6
+
+
+@pytest.mark.parametrize("name,backend,k", [BACKENDS[0], BACKENDS[1], BACKENDS[2], BACKENDS[5], BACKENDS[8]])
+@pytest.mark.parametrize("W,H", [(2048, 3000), (250, 190), (37, 5), (1, 1), (4100, 1100)])
+def test_step_host_band_pipeline_matches_oracle(tws, oracle_omp, W, H, name, backend, k):
+    """tws_step_host (band-pipelined upload / step / readback, several bands at 2048x3000 and
+    4100x1100) against the oracle driven the same way: the host owns the water layer, edits it
+    between steps, and gets depth + flow vector back each step."""
+    h, d = bumpy(W, H, seed=11)
+    c = oracle_omp.derive_consts(float(W), W)
+    t, f, v = new_state(h, d)
+    rng = np.random.default_rng(3)
+    with make_sim(tws, W, H, backend, k) as sim:
+        sim.upload(tws.FIELD_TERRAIN, h)
+        water = d.copy()
+        vel = np.empty((H, W, 2), np.float16)
+        for step in range(4):
+            if step == 2:                               # host-side edit of the water layer between steps
+                edit = (rng.random((H, W)) > 0.9).astype(np.float32)
+                water += edit
+                t[..., 3] += edit
+            if step == 3:                               # NULL input: keep the resident water; separate output buffer
+                out = np.empty_like(water)
+                sim.step_host(None, out, vel)
+                water = out
+            else:
+                sim.step_host(water, water, vel)        # in place: water_out aliases water_in
+            oracle_omp.step(t, f, v, c, 1)
+            assert np.array_equal(bits(water), bits(np.ascontiguousarray(t[..., 3]))), f"{name} step {step}: depth differs"
+            assert np.array_equal(bits(vel), bits(v)), f"{name} step {step}: velocity differs"
+        assert_state_equal(sim, tws, t, f, v, f"{name} resident state after step_host")
+        sim.step(3)                                     # and the resident state carries on in ordinary steps
+        oracle_omp.step(t, f, v, c, 3)
+        assert_state_equal(sim, tws, t, f, v, f"{name} step after step_host")
+        sim.step_host(None, None, None)                 # outputs are optional
+        oracle_omp.step(t, f, v, c, 1)
+        assert_state_equal(sim, tws, t, f, v, f"{name} step_host without outputs")
