@@ -59,10 +59,14 @@ struct StreamCfg {
 //     a waiting warp polls its two neighbours' words (ld.acquire, broadcast LDS).
 // ------------------------------------------------------------------------------------------
 #ifndef TWS_STREAM_WAIT
-#define TWS_STREAM_WAIT 4
+#define TWS_STREAM_WAIT 5
 #endif
+#define TWS_STREAM_EVT (TWS_STREAM_WAIT == 4 || TWS_STREAM_WAIT == 5)   // event-mbarrier protocol (5: tight single-barrier wait loops)
 #ifndef TWS_STREAM_SUSPEND_NS
 #define TWS_STREAM_SUSPEND_NS 20000
+#endif
+#ifndef TWS_STREAM_NOHINT
+#define TWS_STREAM_NOHINT 0    // 1: try_wait without a suspend-time hint (hardware default time limit)
 #endif
 #ifndef TWS_STREAM_L2PROMO
 #define TWS_STREAM_L2PROMO 0   // 0: none, 1: 128 B, 2: 256 B
@@ -88,9 +92,40 @@ struct RowSync {
   bool up_on;             // false for the first row of a piece (nobody above)
 
   // rows idx-1 and idx+1 have finished the half-pass before the one about to run
+  // One barrier, one tight PTX loop: try_wait (hardware suspend), loop back on failure.  A waiting
+  // warp re-issues 5 instructions per wake-up instead of the 14 of the two-barrier C loop below —
+  // waiting warps share their scheduler with working ones, so every spin instruction is stolen from a
+  // row that could make progress.  The bounded spin count turns a protocol bug into a trap, not a hang.
+  static __device__ __forceinline__ void wait_one(uint32_t bar, uint32_t par) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
+        "TWS_WAIT_LOOP:\n"
+#if TWS_STREAM_NOHINT
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#else
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+#endif
+        "@p bra TWS_WAIT_DONE;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.gt.u32 q, n, 4194304;\n"
+        "@q trap;\n"
+        "bra TWS_WAIT_LOOP;\n"
+        "TWS_WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(par), "r"((uint32_t)TWS_STREAM_SUSPEND_NS) : "memory");
+  }
+
   __device__ __forceinline__ void wait() {
     uint32_t spins = 0;
-#if TWS_STREAM_WAIT == 4
+#if TWS_STREAM_WAIT == 5
+    // the row below is the one that lags (it started later); the row above is almost always done
+    wait_one(dn, pd);
+    if (up_on) wait_one(up, pu);
+    up += 16; dn += 16;
+    (void)spins;
+#elif TWS_STREAM_WAIT == 4
     uint32_t done;
     const uint32_t a = up_on ? up : dn, pa = up_on ? pu : pd;
     do {
@@ -116,7 +151,7 @@ struct RowSync {
   // this row has finished a half-pass: every lane's shared-memory stores are ordered before the release
   __device__ __forceinline__ void signal(int lane) {
     __syncwarp();
-#if TWS_STREAM_WAIT == 4
+#if TWS_STREAM_EVT
     if (lane == 0) mbar_arrive(me);
     me += 16;
 #else
@@ -376,7 +411,7 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
       const int idx = t * NW + warp;
       const uint32_t turn = turn_base + (uint32_t)t;
       RowSync sy;
-#if TWS_STREAM_WAIT == 4
+#if TWS_STREAM_EVT
       // neighbours' turns: the row above a slot-0 row lives in the previous turn, the row below a last-slot row in the next
       const uint32_t tu = warp == 0 ? turn - 1u : turn, td = warp == NW - 1 ? turn + 1u : turn;
       sy.up = smem_u32(&evt[wup][0][tu & 1u]); sy.pu = (tu >> 1) & 1u;
@@ -455,7 +490,7 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
           }
           sy.signal(lane);
         }
-#if TWS_STREAM_WAIT == 4
+#if TWS_STREAM_EVT
         if (lane == 0)                                    // the half-passes this feeder row skipped
           for (; s <= 2 * K; ++s) { mbar_arrive(sy.me); sy.me += 16; }
 #endif
