@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=8192, help="grid width (and per-GPU rows unless --strong)")
     ap.add_argument("--strong", action="store_true", help="fixed size x size grid split over the ranks (strong scaling)")
-    ap.add_argument("--backend", default="tb", choices=["unfused", "fused", "tb", "stream"])
+    ap.add_argument("--backend", default="tb", choices=["unfused", "fused", "tb", "stream", "band"])
     ap.add_argument("--tb", type=int, default=2, help="temporal block (steps per launch) for --backend tb / stream")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the end-to-end leg (default min(steps, 40))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -199,7 +199,7 @@ def workload_config(args, world):
     return {
         "workload": f"{W}x{Hg} reference-scene fBm terrain (value noise octaves 2..10, persistence 0.43, seed 231656522) + central lake, "
                     f"open (reference) boundary, no sources; BASELINE config {'4/5 (strong)' if args.strong else '3 per GPU'}",
-        "grid": [W, Hg], "backend": args.backend, "temporal_block": args.tb if args.backend in ("tb", "stream") else 1,
+        "grid": [W, Hg], "backend": args.backend, "temporal_block": args.tb if args.backend in ("tb", "stream", "band") else 1,
         "decomposition": f"{world} row strip(s), halo rows pushed over NVLink by the step kernels' stream (no collective)",
         "l2": "state >= 3.2 GB per GPU, far larger than the 126 MB L2 (inputs larger than L2, no flush needed)",
     }
@@ -232,8 +232,8 @@ def run_b200(args):
     Hg = args.size if args.strong else args.size * world
     plan = tws.plan_strips(Hg, world)
     backend = {"unfused": tws.BACKEND_UNFUSED, "fused": tws.BACKEND_FUSED, "tb": tws.BACKEND_FUSED_TB,
-               "stream": tws.BACKEND_STREAM_TB}[args.backend]
-    k = args.tb if args.backend in ("tb", "stream") else 1
+               "stream": tws.BACKEND_STREAM_TB, "band": tws.BACKEND_BAND_TB}[args.backend]
+    k = args.tb if args.backend in ("tb", "stream", "band") else 1
     sim = tws.Terrain(W, height=Hg, rows=plan.rows(rank), backend=backend, temporal_block=k, device=local)
     tws.connect_strips(sim, plan, rank)
     sim.CreateHeightmapFromNoiseAndResetSim()
@@ -291,10 +291,10 @@ def run_b200(args):
     launch_ms = ms_dev / max(1, (args.steps + k - 1) // k)
     algo_bytes_per_launch = ALGO_BYTES_PER_CELL_UPDATE * cells_local * min(k, args.steps)
     achieved = algo_bytes_per_launch / (launch_ms * 1e-3) / 1e9
-    tag = {"unfused": "unfused", "fused": "fused_k1", "tb": f"fused_k{k}", "stream": f"stream_k{k}"}[args.backend]
+    tag = {"unfused": "unfused", "fused": "fused_k1", "tb": f"fused_k{k}", "stream": f"stream_k{k}", "band": f"band_k{k}"}[args.backend]
     traffic = ncu_traffic_per_launch(tag) if (W == 8192 and sim.rows == 8192) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": {"unfused": "unfused_update_kernel+unfused_apply_kernel", "stream": "stream_step_kernel"}.get(args.backend, "fused_step_kernel"),
+                "kernel": {"unfused": "unfused_update_kernel+unfused_apply_kernel", "stream": "stream_step_kernel", "band": "band_step_kernel"}.get(args.backend, "fused_step_kernel"),
                 "peak_source": peak_src, "algorithmic_bytes_per_cell_update": ALGO_BYTES_PER_CELL_UPDATE,
                 "cell_updates_per_launch": cells_local * min(k, args.steps), "avg_launch_ms": launch_ms,
                 "note": "achieved = 48 B x cell-updates per launch / launch time; with temporal blocking (k steps per HBM round trip) real DRAM traffic is ~48/k B per cell-update, so frac may exceed 1"}

@@ -50,9 +50,11 @@ typedef enum tws_backend {
   TWS_BACKEND_FUSED = 2,    /* one TMA-staged shared-memory stencil kernel per step      */
   TWS_BACKEND_FUSED_TB = 3, /* fused + temporal blocking: `temporal_block` steps per HBM
                                round trip, overlapped square tiles (halo rows recomputed) */
-  TWS_BACKEND_STREAM_TB = 4 /* fused + temporal blocking as a row-streaming pipeline: one warp
+  TWS_BACKEND_STREAM_TB = 4,/* fused + temporal blocking as a row-streaming pipeline: one warp
                                per grid row, rows skewed in time instead of recomputed,
                                `temporal_block` steps per HBM round trip                  */
+  TWS_BACKEND_BAND_TB = 5   /* the same skewed row streaming run in lock step: bands of rows,
+                               one __syncthreads per half-pass instead of per-row barriers */
 } tws_backend;
 
 typedef enum tws_boundary {
@@ -89,7 +91,7 @@ typedef struct tws_params {
   float    flow_acceleration; /* Terrain::SetFlowAcceleration,   default 10                  */
   int32_t  boundary;          /* tws_boundary                                                */
   int32_t  backend;           /* tws_backend                                                 */
-  int32_t  temporal_block;    /* steps fused per launch for FUSED_TB / STREAM_TB (1..4); ignored otherwise */
+  int32_t  temporal_block;    /* steps fused per launch for FUSED_TB / STREAM_TB / BAND_TB (1..4); ignored otherwise */
   int32_t  device;            /* CUDA device ordinal                                         */
   float    rain_rate;         /* EXTENSION: uniform depth added per second (0 = off)         */
   float    evaporation_rate;  /* EXTENSION: uniform depth removed per second (0 = off)       */

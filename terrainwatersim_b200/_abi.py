@@ -21,6 +21,7 @@ BACKEND_UNFUSED = 1
 BACKEND_FUSED = 2
 BACKEND_FUSED_TB = 3
 BACKEND_STREAM_TB = 4
+BACKEND_BAND_TB = 5
 
 BOUNDARY_REFERENCE_OPEN = 0
 BOUNDARY_CLOSED = 1

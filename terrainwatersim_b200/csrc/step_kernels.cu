@@ -530,6 +530,46 @@ cudaError_t build_tma_boxes(const Geom& g, const Planes& p, int side, int box_x,
   return cudaSuccess;
 }
 
+// Row descriptors of the streaming kernels: m[0] = terrain (2-D, box box_x x 1), m[1] = the five state
+// planes d, F+X, F-X, F+Y, F-Y of side `side` as ONE 3-D tensor (x, row, plane; box box_x x 1 x 5) —
+// layout_planes() keeps them consecutive with a uniform stride.  Same row visibility as build_tma_boxes.
+cudaError_t build_tma_rows(const Geom& g, const Planes& p, int side, int box_x, TmaSet* out, std::string* err, int l2_promotion) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { if (err) *err = "cuTensorMapEncodeTiled not available from the driver"; return cudaErrorNotSupported; }
+  const int first_row = g.has_up ? 0 : TWS_HALO_ROWS;
+  const int vis_rows = g.rows + (g.has_up ? TWS_HALO_ROWS : 0) + (g.has_down ? TWS_HALO_ROWS : 0);
+  const CUtensorMapL2promotion promo = l2_promotion == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                     : l2_promotion == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+  const ptrdiff_t plane_stride = (const char*)p.F[side][0] - (const char*)p.d[side];
+  for (int i = 0; i < 4; ++i)
+    if ((const char*)p.F[side][i] - (const char*)p.d[side] != (i + 1) * plane_stride) {
+      if (err) *err = "state planes are not uniformly strided";
+      return cudaErrorInvalidValue;
+    }
+  CUresult r;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)g.W, (cuuint64_t)vis_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)g.pitch * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)box_x, 1};
+    cuuint32_t estr[2] = {1, 1};
+    r = enc(&out->m[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.h + (size_t)first_row * g.pitch, dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r == CUDA_SUCCESS) {
+    cuuint64_t dims[3] = {(cuuint64_t)g.W, (cuuint64_t)vis_rows, 5};
+    cuuint64_t strides[2] = {(cuuint64_t)g.pitch * sizeof(float), (cuuint64_t)plane_stride};
+    cuuint32_t box[3] = {(cuuint32_t)box_x, 1, 5};
+    cuuint32_t estr[3] = {1, 1, 1};
+    r = enc(&out->m[1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.d[side] + (size_t)first_row * g.pitch, dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+    return cudaErrorInvalidValue;
+  }
+  return cudaSuccess;
+}
+
 cudaError_t fused_build_tma(int K, const Geom& g, const Planes& p, int side, TmaSet* out, std::string* err) {
   int sx, sy;
   box_for(K, &sx, &sy);

@@ -29,11 +29,16 @@
 
 namespace tws {
 
+#ifndef TWS_STREAM_HX_MIN
+#define TWS_STREAM_HX_MIN 8    // tuning: widen the x halo so that the output columns of a strip start on a 64 / 128 B boundary
+#endif
+constexpr int stream_hx(int K) { return ((2 * K + 3) / 4) * 4 > TWS_STREAM_HX_MIN ? ((2 * K + 3) / 4) * 4 : TWS_STREAM_HX_MIN; }
+
 template <int K_, int NW_, int G_>
 struct StreamCfg {
   static constexpr int K = K_, NW = NW_, NT = NW_ * 32, G = G_;
   static constexpr int SXW = 128 * G;                   // staged strip width: G float4 groups per lane
-  static constexpr int HX = ((2 * K + 3) / 4) * 4;      // x halo rounded to whole float4 groups
+  static constexpr int HX = stream_hx(K);               // x halo rounded to whole float4 groups
   static constexpr int OX = SXW - 2 * HX;               // output columns per strip
   static constexpr int NHP = 2 * K + 1;                 // half-passes per row, the load included
   static constexpr int LAND = 6 * SXW;                  // floats per landing buffer (h, d, F x4)
@@ -58,6 +63,12 @@ struct StreamCfg {
 //   0 — progress words: each slot publishes `rows done * NHP + half-passes done` (st.release) and
 //     a waiting warp polls its two neighbours' words (ld.acquire, broadcast LDS).
 // ------------------------------------------------------------------------------------------
+#ifndef TWS_DBG_NOFENCE
+#define TWS_DBG_NOFENCE 0   // tuning experiment only
+#endif
+#ifndef TWS_DBG_NOSTORE
+#define TWS_DBG_NOSTORE 0   // tuning experiment only: 1 drops the HBM stores (wrong results)
+#endif
 #ifndef TWS_STREAM_WAIT
 #define TWS_STREAM_WAIT 5
 #endif
@@ -82,6 +93,23 @@ __device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t addr) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+
+// Shared-memory float4 access through 32-bit shared-window addresses.  The exchange-slot addresses are
+// kept as opaque 32-bit values: left as generic pointers derived from the warp index, the compiler
+// re-derives them (shared-window base, slot selects, multiplies: ~35 integer instructions) in every
+// half-pass rather than spend three registers on them.
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t keep_u32(uint32_t v) {       // pins a value in a register (no rematerialisation)
+  asm volatile("" : "+r"(v));
+  return v;
 }
 
 // Per-row synchronisation cursor: advanced by one half-pass per wait() / signal().
@@ -204,9 +232,9 @@ __device__ __forceinline__ float apply_cell_t(float depth, float fx, float fy, f
 
 // flowUpdate.comp:34-62 for the lane's 4*G cells.  Reads the neighbour rows' water level, leaves the
 // new outflow in registers, publishes its +-Y components; LAST also stores the flux planes to HBM.
-// The three slot pointers address this lane's first group in plane 0 (H) of the slot.
+// The three slot addresses (32-bit shared window, bytes) are this lane's first group in plane 0 (H) of the slot.
 template <int G, int SXW, bool EDGE, bool LAST>
-__device__ __forceinline__ void stream_flux(const float* __restrict__ up, const float* __restrict__ dn, float* __restrict__ me, const int lane,
+__device__ __forceinline__ void stream_flux(const uint32_t up, const uint32_t dn, const uint32_t me, const int lane,
                                             const float4 (&h)[G], const float4 (&d)[G], float4 (&fx)[G], float4 (&fy)[G], float4 (&fz)[G],
                                             float4 (&fw)[G], const RowCtx<G>& rc, const FusedOut& out, const Geom& g, const StepConsts& c) {
   float4 HC[G], HU[G], HD[G];
@@ -214,8 +242,8 @@ __device__ __forceinline__ void stream_flux(const float* __restrict__ up, const 
 #pragma unroll
   for (int q = 0; q < G; ++q) {
     HC[q] = add4(d[q], h[q]);                                                        // a + r, flowUpdate.comp:34
-    HU[q] = ld4(up + 128 * q);
-    HD[q] = ld4(dn + 128 * q);
+    HU[q] = lds4(up + 512 * q);
+    HD[q] = lds4(dn + 512 * q);
     w3[q] = HC[q].w; x0[q] = HC[q].x;
   }
   x_neighbours<G>(w3, x0, lane, HL, HR);
@@ -273,9 +301,9 @@ __device__ __forceinline__ void stream_flux(const float* __restrict__ up, const 
       pfz[i] = __fmul_rn(pfz[i], scale[q][i]); pfw[i] = __fmul_rn(pfw[i], scale[q][i]);
       if (EDGE && !(rc.row_in && (unsigned)(rc.gx[q] + i) < (unsigned)g.W)) { pfx[i] = 0.f; pfy[i] = 0.f; pfz[i] = 0.f; pfw[i] = 0.f; }
     }
-    st4(me + SXW + 128 * q, fz[q]);              // plane 1: +Y outflow, read by the row below
-    st4(me + 2 * SXW + 128 * q, fw[q]);          // plane 2: -Y outflow, read by the row above
-    if (LAST && rc.store && rc.st[q]) {
+    sts4(me + 4 * SXW + 512 * q, fz[q]);         // plane 1: +Y outflow, read by the row below
+    sts4(me + 8 * SXW + 512 * q, fw[q]);         // plane 2: -Y outflow, read by the row above
+    if (LAST && rc.store && rc.st[q] && !TWS_DBG_NOSTORE) {
       st4(out.F[0] + rc.go[q], fx[q]); st4(out.F[1] + rc.go[q], fy[q]); st4(out.F[2] + rc.go[q], fz[q]); st4(out.F[3] + rc.go[q], fw[q]);
     }
   }
@@ -285,7 +313,7 @@ __device__ __forceinline__ void stream_flux(const float* __restrict__ up, const 
 // new depth stays in registers and the new water level is published; LAST: depth and the packed
 // fp16 flow vector go to HBM.
 template <int G, int SXW, bool EDGE, bool LAST, bool EXT>
-__device__ __forceinline__ void stream_depth(const float* __restrict__ up, const float* __restrict__ dn, float* __restrict__ me, const int lane,
+__device__ __forceinline__ void stream_depth(const uint32_t up, const uint32_t dn, const uint32_t me, const int lane,
                                              const float4 (&h)[G], float4 (&d)[G], const float4 (&fx)[G], const float4 (&fy)[G],
                                              const float4 (&fz)[G], const float4 (&fw)[G], const RowCtx<G>& rc, const FusedOut& out,
                                              const Geom& g, const StepConsts& c) {
@@ -293,8 +321,8 @@ __device__ __forceinline__ void stream_depth(const float* __restrict__ up, const
   float w3[G], x0[G], l[G], r[G];
 #pragma unroll
   for (int q = 0; q < G; ++q) {
-    iy1[q] = ld4(dn + 2 * SXW + 128 * q);      // F(x,y+1).w, flowApply.comp:34
-    iy0[q] = ld4(up + SXW + 128 * q);          // F(x,y-1).z, :35
+    iy1[q] = lds4(dn + 8 * SXW + 512 * q);     // F(x,y+1).w, flowApply.comp:34
+    iy0[q] = lds4(up + 4 * SXW + 512 * q);     // F(x,y-1).z, :35
     w3[q] = fx[q].w; x0[q] = fy[q].x;
   }
   // F(x-1,y).x (:33) is the left cell's +X outflow, F(x+1,y).y (:32) the right cell's -X outflow
@@ -321,8 +349,8 @@ __device__ __forceinline__ void stream_depth(const float* __restrict__ up, const
     }
     if (!LAST) {
       d[q] = make_float4(nd[0], nd[1], nd[2], nd[3]);
-      st4(me + 128 * q, add4(d[q], h[q]));
-    } else if (rc.store && rc.st[q]) {
+      sts4(me + 512 * q, add4(d[q], h[q]));
+    } else if (rc.store && rc.st[q] && !TWS_DBG_NOSTORE) {
       st4(out.d + rc.go[q], make_float4(nd[0], nd[1], nd[2], nd[3]));
       *reinterpret_cast<uint4*>(out.v + rc.go[q]) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
     }
@@ -331,11 +359,7 @@ __device__ __forceinline__ void stream_depth(const float* __restrict__ up, const
 
 template <class C, bool EXT>
 __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_constant__ CUtensorMap tm_h,
-                                                               const __grid_constant__ CUtensorMap tm_d,
-                                                               const __grid_constant__ CUtensorMap tm_f0,
-                                                               const __grid_constant__ CUtensorMap tm_f1,
-                                                               const __grid_constant__ CUtensorMap tm_f2,
-                                                               const __grid_constant__ CUtensorMap tm_f3,
+                                                               const __grid_constant__ CUtensorMap tm_s,
                                                                FusedOut out, Geom g, StepConsts c, int lr0, int lr1, int nstrips,
                                                                int tma_y_bias) {
   constexpr int K = C::K, NW = C::NW, G = C::G, SXW = C::SXW, HX = C::HX, OX = C::OX, NHP = C::NHP, LAND = C::LAND;
@@ -349,10 +373,10 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
   // lane-resolved pointers: landing buffer; exchange slots [NW][H | F+Y | F-Y][SXW] of this row and its neighbours
   float* land = smem + warp * LAND;
   const float* land_l = land + lane * 4;
-  float* xch = smem + NW * LAND + lane * 4;
-  float* x_me = xch + warp * C::XROW;
-  const float* x_up = xch + wup * C::XROW;
-  const float* x_dn = xch + wdn * C::XROW;
+  const uint32_t xch = smem_u32(smem + NW * LAND + lane * 4);
+  const uint32_t x_me = xch + warp * C::XROW * 4;
+  const uint32_t x_up = xch + wup * C::XROW * 4;
+  const uint32_t x_dn = xch + wdn * C::XROW * 4;
 
   if (tid == 0) {
 #pragma unroll 1
@@ -386,15 +410,12 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
     __syncthreads();
 
     auto issue = [&](int y) {                             // one lane: land row y in this warp's buffer
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (!TWS_DBG_NOFENCE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&full[warp], (uint32_t)(LAND * sizeof(float)));
       const int ty = y + tma_y_bias;
       tma_load_2d(land, &tm_h, sx0, ty, &full[warp]);
-      tma_load_2d(land + SXW, &tm_d, sx0, ty, &full[warp]);
-      tma_load_2d(land + 2 * SXW, &tm_f0, sx0, ty, &full[warp]);
-      tma_load_2d(land + 3 * SXW, &tm_f1, sx0, ty, &full[warp]);
-      tma_load_2d(land + 4 * SXW, &tm_f2, sx0, ty, &full[warp]);
-      tma_load_2d(land + 5 * SXW, &tm_f3, sx0, ty, &full[warp]);
+
+      tma_load_3d(land + SXW, &tm_s, sx0, ty, 0, &full[warp]);     // d, F+X, F-X, F+Y, F-Y in one operation
     };
     if (lane == 0 && warp < nrows) issue(ystart + warp);
 
@@ -454,7 +475,7 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
       __syncwarp();
       if (lane == 0 && idx + NW < nrows) issue(y + NW);
 #pragma unroll
-      for (int q = 0; q < G; ++q) st4(x_me + 128 * q, add4(d[q], h[q]));
+      for (int q = 0; q < G; ++q) sts4(x_me + 512 * q, add4(d[q], h[q]));
       sy.signal(lane);
 
       if (!edge && smax == 2 * K) {
@@ -497,6 +518,232 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
       }
     }
     turn_base += (uint32_t)turns;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Band kernel: the same row streaming, synchronised by the CTA instead of per-row barriers.
+// ------------------------------------------------------------------------------------------
+// The ring kernel above keeps NW rows in flight and lets each advance as soon as its two neighbours
+// allow; its throughput is capped by the dependency cone: only NW - 2K of the NW row slots make
+// progress per ring turn, and every half-pass pays a wake-up latency (ncu: 35 % of the warp samples
+// sit in the neighbour waits).  The band kernel runs the same skewed schedule in lock step:
+//
+//   * a column strip is marched in BANDS of NW rows, row i of the piece belongs to warp i % NW;
+//   * half-pass s of a band updates the NW consecutive rows (Yb - NW - s, Yb - s] (Yb = last row of the
+//     band): the window slides up by one row per half-pass, which is exactly the skew the data
+//     dependency needs (row y at half-pass s reads rows y-1, y+1 after half-pass s-1) — no row is ever
+//     recomputed, and a window of NW consecutive rows holds exactly one row of every warp: all warps
+//     work in every half-pass, there is nothing to wait for but the __syncthreads between half-passes;
+//   * a warp w < NW - 2K finishes its row inside the band.  The last 2K warps ("carriers") get through
+//     NW-1-w half-passes only; they park the new row in shared memory, pick the row they parked in
+//     the previous band up again and finish that one (half-passes NW-w .. 2K).  Row state lives in
+//     registers while it is worked on (24 per lane and float4 group, as in the ring kernel);
+//   * the exchange slot (H | F+Y | F-Y) of a row must outlive the band when the row below is carried,
+//     so the last 2K+1 warps alternate between two slots by band parity;
+//   * TMA lands a warp's next row (one band ahead) in its private landing buffer while the current
+//     band is computed; out-of-bounds zero fill is the reference's exterior rule, as everywhere.
+template <int K_, int NW_, int G_, int NGRP_>
+struct BandCfg {
+  // NGRP independent groups of NW warps share the CTA: each marches its own pieces with its own named
+  // barrier, so one group's barrier waits and store bursts overlap the other group's arithmetic.
+  static constexpr int K = K_, NW = NW_, NGRP = NGRP_, NT = NW_ * NGRP_ * 32, G = G_;
+  static constexpr int SXW = 128 * G;
+  static constexpr int HX = stream_hx(K);
+  static constexpr int OX = SXW - 2 * HX;
+  static constexpr int HP = 2 * K;                       // computing half-passes per row
+  static constexpr int NC = HP;                          // carrier warps: NW-HP .. NW-1
+  static constexpr int NDB = HP + 1;                     // warps with a double-buffered exchange slot
+  static constexpr int NSLOT = NW + NDB;
+  static constexpr int LAND = 6 * SXW;                   // floats per landing / parking buffer
+  static constexpr int XROW = 3 * SXW;                   // floats per exchange slot
+  static constexpr int GROUP_FLOATS = NW * LAND + NSLOT * XROW + NC * LAND;
+  static constexpr size_t SMEM = (size_t)NGRP * GROUP_FLOATS * sizeof(float);
+  static_assert(NW >= HP + 1, "a band must be deeper than the dependency cone");
+  static_assert(SMEM <= 227 * 1024, "band configuration does not fit in shared memory");
+};
+
+template <class C>
+__device__ __forceinline__ int band_slot_base(int w) {   // first exchange slot of warp w's rows
+  return w < C::NW - C::NDB ? w : (C::NW - C::NDB) + 2 * (w - (C::NW - C::NDB));
+}
+
+template <class C, bool EXT>
+__global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_constant__ CUtensorMap tm_h,
+                                                             const __grid_constant__ CUtensorMap tm_s,
+                                                             FusedOut out, Geom g, StepConsts c, int lr0, int lr1, int nstrips,
+                                                             int tma_y_bias) {
+  constexpr int K = C::K, NW = C::NW, G = C::G, SXW = C::SXW, HX = C::HX, OX = C::OX, HP = C::HP, LAND = C::LAND, XROW = C::XROW;
+  extern __shared__ __align__(1024) float smem[];
+  __shared__ uint64_t full_all[NW * C::NGRP];
+  // read through volatile asm: the thread index stays in a register instead of being re-read (S2R, ~20
+  // cycles of latency) and re-derived in every half-pass
+  uint32_t tid_u;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_u));
+  const int tid = (int)tid_u, lane = tid & 31, grp = (tid >> 5) / NW, warp = (tid >> 5) - grp * NW;   // warp: index inside the group
+  float* gsm = smem + grp * C::GROUP_FLOATS;              // this group's landing buffers | exchange slots | parking
+  uint64_t* full = full_all + grp * NW;
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(NW * 32) : "memory"); };
+  float* land = gsm + warp * LAND;
+  const float* land_l = land + lane * 4;
+  const uint32_t xch = smem_u32(gsm + NW * LAND + lane * 4);
+  const int pw = (NW - 1 - warp) < HP ? (NW - 1 - warp) : HP;     // half-passes the new row gets inside its own band
+  const bool carrier = pw < HP;
+  float* park = gsm + NW * LAND + C::NSLOT * XROW + (carrier ? warp - (NW - C::NC) : 0) * LAND + lane * 4;
+  // exchange slots of this warp's rows and of the rows above / below them: slot = base + (band & 1 if double buffered)
+  const int wu = warp == 0 ? NW - 1 : warp - 1, ju = warp == 0 ? -1 : 0;          // the row above a warp-0 row belongs to the previous band
+  const int wd = warp == NW - 1 ? 0 : warp + 1, jd = warp == NW - 1 ? 1 : 0;      // the row below a last-warp row to the next one
+  const int sb_me = band_slot_base<C>(warp) * XROW * 4, sb_up = band_slot_base<C>(wu) * XROW * 4, sb_dn = band_slot_base<C>(wd) * XROW * 4;
+  const int db_me = warp >= NW - C::NDB ? XROW * 4 : 0, db_up = wu >= NW - C::NDB ? XROW * 4 : 0, db_dn = wd >= NW - C::NDB ? XROW * 4 : 0;
+
+  if (tid == 0) {
+#pragma unroll 1
+    for (int i = 0; i < NW * C::NGRP; ++i) mbar_init(&full_all[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();                                        // the only CTA-wide barrier: the mbarriers exist
+  uint32_t parity = 0;
+
+  const long long R = (long long)(lr1 - lr0);
+  const long long TR = R * nstrips;
+  const long long vcta = (long long)blockIdx.x * C::NGRP + grp, nvcta = (long long)gridDim.x * C::NGRP;   // every group is a virtual CTA
+  const long long lin_begin = TR * vcta / nvcta, lin_end = TR * (vcta + 1) / nvcta;
+
+#pragma unroll 1
+  for (long long lin = lin_begin; lin < lin_end;) {
+    const int strip = (int)(lin / R);
+    const int ya = lr0 + (int)(lin - (long long)strip * R);
+    const int yb = (int)((long long)ya + (lin_end - lin) < (long long)lr1 ? (long long)ya + (lin_end - lin) : (long long)lr1);
+    lin += yb - ya;
+    const int sx0 = strip * OX - HX;
+    const int ystart = ya - HP;                           // 2K warm-up rows above, 2K feeder rows below
+    const int N = (yb - ya) + 2 * HP;
+    const int J = (N + NW - 1) / NW;                      // bands that load rows; band J only finishes the carried ones
+    const bool xedge = sx0 < 0 || sx0 + SXW > g.W;
+
+    group_sync();                                         // every warp of the group is done with the previous piece
+
+    auto issue = [&](int y) {                             // one lane: land row y in this warp's buffer
+      if (!TWS_DBG_NOFENCE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&full[warp], (uint32_t)(LAND * sizeof(float)));
+      const int ty = y + tma_y_bias;
+      tma_load_2d(land, &tm_h, sx0, ty, &full[warp]);
+
+      tma_load_3d(land + SXW, &tm_s, sx0, ty, 0, &full[warp]);     // d, F+X, F-X, F+Y, F-Y in one operation
+    };
+    if (lane == 0 && warp < N) issue(ystart + warp);
+
+    RowCtx<G> rc;
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      const int o = (lane + 32 * q) * 4;
+      rc.gx[q] = sx0 + o;
+      rc.st[q] = o >= HX && o < HX + OX && rc.gx[q] < g.pitch;
+    }
+
+    // the row this warp is working on: registers + where it exchanges with its neighbours
+    float4 h[G], d[G], fx[G], fy[G], fz[G], fw[G];
+    bool valid = false, plain = false;                    // plain: interior row that runs all 2K half-passes
+    int smax = 0;
+    uint32_t x_me = xch, x_up = xch, x_dn = xch;
+    auto set_row = [&](int jj, int i) {                   // piece row i of band jj (i < 0 or >= N: no row)
+      valid = i >= 0 && i < N;
+      const int y = ystart + i;
+      rc.gy = g.row0 + y;
+      rc.row_in = (unsigned)rc.gy < (unsigned)g.Hg;
+      rc.store = y >= ya && y < yb;
+      const size_t rowoff = (size_t)((long long)y * g.pitch);      // only dereferenced when rc.store (y >= 0)
+#pragma unroll
+      for (int q = 0; q < G; ++q) rc.go[q] = rowoff + rc.gx[q];
+      // rows below the piece only feed the rows above them: row yb-1+m stops after half-pass 2K-m
+      smax = (y < yb) ? HP : HP - (y - yb + 1);
+      plain = !(xedge || rc.gy <= 0 || rc.gy >= g.Hg - 1) && smax == HP;
+      x_me = keep_u32(xch + sb_me + ((jj & 1) ? db_me : 0));
+      x_up = keep_u32(xch + sb_up + (((jj + ju) & 1) ? db_up : 0));
+      x_dn = keep_u32(xch + sb_dn + (((jj + jd) & 1) ? db_dn : 0));
+    };
+    // park the new row, resume the row parked one band ago (plane by plane through one temporary)
+    auto swap_rows = [&](int jj, bool hasB) {
+      const int iA = (jj - 1) * NW + warp;
+#pragma unroll
+      for (int q = 0; q < G; ++q) {
+        float* pk = park + 128 * q;
+        float4 t;
+        t = ld4(pk);           if (hasB) st4(pk, h[q]);            h[q] = t;
+        t = ld4(pk + SXW);     if (hasB) st4(pk + SXW, d[q]);      d[q] = t;
+        t = ld4(pk + 2 * SXW); if (hasB) st4(pk + 2 * SXW, fx[q]); fx[q] = t;
+        t = ld4(pk + 3 * SXW); if (hasB) st4(pk + 3 * SXW, fy[q]); fy[q] = t;
+        t = ld4(pk + 4 * SXW); if (hasB) st4(pk + 4 * SXW, fz[q]); fz[q] = t;
+        t = ld4(pk + 5 * SXW); if (hasB) st4(pk + 5 * SXW, fw[q]); fw[q] = t;
+      }
+      set_row(jj - 1, (jj > 0 && iA < N) ? iA : -1);
+    };
+
+#pragma unroll 1
+    for (int j = 0; j <= J; ++j) {
+      const int iB = j * NW + warp;
+      const bool hasB = iB < N;
+      set_row(j, iB);
+      // ---- half-pass 0: registers <- landing buffer; publish H; prefetch this warp's row of the next band ----
+      if (hasB) {
+        mbar_wait(&full[warp], parity);
+        parity ^= 1u;
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+          h[q] = ld4(land_l + 128 * q);            d[q] = ld4(land_l + SXW + 128 * q);
+          fx[q] = ld4(land_l + 2 * SXW + 128 * q); fy[q] = ld4(land_l + 3 * SXW + 128 * q);
+          fz[q] = ld4(land_l + 4 * SXW + 128 * q); fw[q] = ld4(land_l + 5 * SXW + 128 * q);
+        }
+        __syncwarp();
+        if (lane == 0 && iB + NW < N) issue(ystart + iB + NW);
+#pragma unroll
+        for (int q = 0; q < G; ++q) sts4(x_me + 512 * q, add4(d[q], h[q]));
+      }
+      group_sync();
+
+      if (!carrier && plain && valid) {
+        // ---- the common case: an interior row that starts and finishes inside this band ----
+#pragma unroll 1
+        for (int lv = 1; lv < K; ++lv) {
+          stream_flux<G, SXW, false, false>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+          group_sync();
+          stream_depth<G, SXW, false, false, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+          group_sync();
+        }
+        stream_flux<G, SXW, false, true>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+        group_sync();
+        stream_depth<G, SXW, false, true, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+        group_sync();
+      } else {
+        // ---- carriers (two rows per band), rows on the grid edge, feeder rows that stop early, no row at all ----
+        const int swap_at = carrier ? pw + 1 : 0;
+#pragma unroll 1
+        for (int s = 1; s <= HP; ++s) {
+          if (s == swap_at) swap_rows(j, hasB);
+          if (valid && s <= smax) {
+            const bool last = s >= HP - 1;
+            if (s & 1) {
+              if (!plain) {
+                if (last) stream_flux<G, SXW, true, true>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+                else stream_flux<G, SXW, true, false>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+              } else {
+                if (last) stream_flux<G, SXW, false, true>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+                else stream_flux<G, SXW, false, false>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+              }
+            } else {
+              if (!plain) {
+                if (last) stream_depth<G, SXW, true, true, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+                else stream_depth<G, SXW, true, false, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+              } else {
+                if (last) stream_depth<G, SXW, false, true, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+                else stream_depth<G, SXW, false, false, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+              }
+            }
+          }
+          group_sync();
+        }
+      }
+    }
   }
 }
 
@@ -545,13 +792,67 @@ static cudaError_t launch_stream_k(const Geom& g, const Planes& p, const TmaSet&
   const int sms = stream_sm_count();
   const int grid = (int)(want < 1 ? 1 : (want < sms ? want : sms));
   const int bias = g.has_up ? TWS_HALO_ROWS : 0;
-  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], tma.m[2], tma.m[3], tma.m[4], tma.m[5], out, g, c, lr0, lr1, nstrips, bias);
+  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], out, g, c, lr0, lr1, nstrips, bias);
   return cudaGetLastError();
 }
 
+#ifndef TWS_BAND_G
+#define TWS_BAND_G 1
+#endif
+#ifndef TWS_BAND_NW
+#define TWS_BAND_NW (24 / TWS_BAND_G)
+#endif
+#ifndef TWS_BAND_NGRP
+#define TWS_BAND_NGRP 2
+#endif
+template <int K> struct BandCfgFor { using type = BandCfg<K, TWS_BAND_NW / TWS_BAND_NGRP, TWS_BAND_G, TWS_BAND_NGRP>; };
+static_assert(BandCfgFor<1>::type::SXW == StreamCfgFor<1>::type::SXW, "ring and band kernels share the row descriptors");
+
+template <int K, bool EXT>
+static cudaError_t launch_band_k(const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
+                                 cudaStream_t st) {
+  using C = typename BandCfgFor<K>::type;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = band_step_kernel<C, EXT>;
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  if (lr1 <= lr0) return cudaSuccess;
+  const int dst = 1 - src;
+  const size_t row0_off = (size_t)TWS_HALO_ROWS * g.pitch;
+  FusedOut out;
+  out.d = p.d[dst] + row0_off;
+  for (int i = 0; i < 4; ++i) out.F[i] = p.F[dst][i] + row0_off;
+  out.v = p.v + row0_off;
+  const int nstrips = (g.W + C::OX - 1) / C::OX;
+  const long long total_rows = (long long)nstrips * (lr1 - lr0);
+  // one persistent CTA per SM; small grids: at least ~4 bands of rows per CTA so the 4K warm-up / feeder rows amortise
+  const long long min_rows = 4 * C::NW * C::NGRP;
+  long long want = (total_rows + min_rows - 1) / min_rows;
+  const int sms = stream_sm_count();
+  const int grid = (int)(want < 1 ? 1 : (want < sms ? want : sms));
+  const int bias = g.has_up ? TWS_HALO_ROWS : 0;
+  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], out, g, c, lr0, lr1, nstrips, bias);
+  return cudaGetLastError();
+}
+
+// impl: 0 = ring kernel (per-row barriers), 1 = band kernel (CTA-synchronous bands)
 cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
-                          cudaStream_t st) {
+                          cudaStream_t st, int impl) {
   const bool ext = c.ext_sources != 0;
+  if (impl == 1) {
+    switch (K) {
+      case 1: return ext ? launch_band_k<1, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<1, false>(g, p, tma, src, c, lr0, lr1, st);
+      case 2: return ext ? launch_band_k<2, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<2, false>(g, p, tma, src, c, lr0, lr1, st);
+      case 3: return ext ? launch_band_k<3, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<3, false>(g, p, tma, src, c, lr0, lr1, st);
+      case 4: return ext ? launch_band_k<4, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<4, false>(g, p, tma, src, c, lr0, lr1, st);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (K) {
     case 1: return ext ? launch_stream_k<1, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<1, false>(g, p, tma, src, c, lr0, lr1, st);
     case 2: return ext ? launch_stream_k<2, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<2, false>(g, p, tma, src, c, lr0, lr1, st);
@@ -564,7 +865,7 @@ cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& t
 // Row descriptors: box = one SXW-cell row segment.  Same visibility rule as the tile kernel's maps
 // (own rows plus the halo rows towards an existing neighbour; everything else zero-filled).
 cudaError_t stream_build_tma(const Geom& g, const Planes& p, int side, TmaSet* out, std::string* err) {
-  return build_tma_boxes(g, p, side, StreamCfgFor<1>::type::SXW, 1, out, err, TWS_STREAM_L2PROMO);
+  return build_tma_rows(g, p, side, StreamCfgFor<1>::type::SXW, out, err, TWS_STREAM_L2PROMO);
 }
 
 }  // namespace tws

@@ -104,11 +104,13 @@ void layout_planes(uint8_t* base, int pitch, int rows, Planes* p, size_t* plane_
   const size_t pb = align_up(elems * sizeof(float), 1024);
   size_t off = TWS_CTRL_BYTES;
   auto take = [&]() { uint8_t* q = base ? base + off : nullptr; off += pb; return q; };
+  // the depth and the four flux planes of one ping-pong side are consecutive with a uniform stride,
+  // so one 3-D TMA descriptor (x, row, plane) fetches a row of all five in a single operation
   p->h = (float*)take();
-  p->d[0] = (float*)take();
-  p->d[1] = (float*)take();
-  for (int s = 0; s < 2; ++s)
+  for (int s = 0; s < 2; ++s) {
+    p->d[s] = (float*)take();
     for (int i = 0; i < 4; ++i) p->F[s][i] = (float*)take();
+  }
   p->v = (uint32_t*)take();
   if (plane_elems) *plane_elems = elems;
   if (total) *total = off;
@@ -118,6 +120,8 @@ int pitch_for(int width) { return (int)align_up((size_t)width, 64); }
 
 // Terrain.cpp:175-198 — see tws_step_constants in tws.h.
 void drop_graphs(tws_sim* s);
+inline bool is_stream_backend(int b) { return b == TWS_BACKEND_STREAM_TB || b == TWS_BACKEND_BAND_TB; }
+inline int stream_impl(const tws_sim* s) { return s->prm.backend == TWS_BACKEND_BAND_TB ? 1 : 0; }
 void derive_constants(tws_sim* s) {
   drop_graphs(s);                                       // captured batches bake the constants in
   const tws_params& p = s->prm;
@@ -219,7 +223,7 @@ tws_status run_block_stream(tws_sim* s, int k) {
   tws_status r = ensure_tma_stream(s);
   if (r) return r;
   if (!strip) {
-    TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, g.rows, s->st_main));
+    TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, g.rows, s->st_main, stream_impl(s)));
     s->launches += 1;
     s->cur = 1 - src;
     return TWS_OK;
@@ -229,13 +233,13 @@ tws_status run_block_stream(tws_sim* s, int k) {
   const int i0 = e_top, i1 = g.rows - e_bot;
   TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));
   if (i1 > i0) {
-    TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i0, i1, s->st_main));
+    TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i0, i1, s->st_main, stream_impl(s)));
     s->launches += 1;
   }
   TWS_CUDA(s, cudaStreamWaitEvent(s->st_edge, s->ev_main, 0));
   TWS_CUDA(s, launch_wait_flags(s->ctrl, g.has_up, g.has_down, s->epoch, s->st_edge)); s->launches++;
-  if (e_top > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, e_top, s->st_edge)); s->launches++; }
-  if (e_bot > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i1, g.rows, s->st_edge)); s->launches++; }
+  if (e_top > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, e_top, s->st_edge, stream_impl(s))); s->launches++; }
+  if (e_bot > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i1, g.rows, s->st_edge, stream_impl(s))); s->launches++; }
   r = push_edges(s, 1 - src, false, s->st_edge); if (r) return r;
   r = post_and_count(s, s->st_edge); if (r) return r;
   TWS_CUDA(s, cudaEventRecord(s->ev_edge, s->st_edge));
@@ -255,7 +259,7 @@ tws_status run_block(tws_sim* s, int k) {
     s->launches += 2;
     return TWS_OK;
   }
-  if (s->prm.backend == TWS_BACKEND_STREAM_TB) return run_block_stream(s, k);
+  if (is_stream_backend(s->prm.backend)) return run_block_stream(s, k);
   tws_status r = ensure_tma(s, k);
   if (r) return r;
   const int tiles = fused_tile_rows(k, g.rows);
@@ -312,9 +316,9 @@ tws_status run_batch_graph(tws_sim* s, int n, int K, bool* done) {
       return TWS_OK;
     }
   // make sure nothing but kernel launches happens inside the capture
-  if (s->prm.backend == TWS_BACKEND_STREAM_TB) {
+  if (is_stream_backend(s->prm.backend)) {
     tws_status r = ensure_tma_stream(s); if (r) return r;
-    for (int k : {K, n % K}) if (k > 0) TWS_CUDA(s, launch_stream(k, s->geom, s->planes, s->tma_stream[0], 0, s->consts, 0, 0, s->st_main));
+    for (int k : {K, n % K}) if (k > 0) TWS_CUDA(s, launch_stream(k, s->geom, s->planes, s->tma_stream[0], 0, s->consts, 0, 0, s->st_main, stream_impl(s)));
   } else if (s->prm.backend != TWS_BACKEND_UNFUSED) {
     for (int k : {K, n % K}) if (k > 0) {
       tws_status r = ensure_tma(s, k); if (r) return r;
@@ -352,7 +356,7 @@ tws_status run_steps(tws_sim* s, int n) {
   const bool strip = g.has_up || g.has_down;
   if (strip && !s->connected) return fail(s, TWS_ERR_STATE, "strip sim stepped before tws_halo_connect");
   TWS_CUDA(s, cudaEventRecord(s->ev_start, s->st_main));
-  const int K = (s->prm.backend == TWS_BACKEND_FUSED_TB || s->prm.backend == TWS_BACKEND_STREAM_TB) ? s->K : 1;
+  const int K = (s->prm.backend == TWS_BACKEND_FUSED_TB || is_stream_backend(s->prm.backend)) ? s->K : 1;
   if (!strip && s->use_graphs && n >= 2 && n <= 64) {
     bool done = false;
     tws_status r = run_batch_graph(s, n, K, &done);
@@ -425,9 +429,9 @@ tws_status tws_create(const tws_params* p, tws_sim** out) {
   if (bad_float(p->flow_acceleration) || p->flow_acceleration < 0.0f) return fail(nullptr, TWS_ERR_INVALID, "tws_create: flow_acceleration must be >= 0");
   if (bad_float(p->rain_rate) || bad_float(p->evaporation_rate) || p->rain_rate < 0.0f || p->evaporation_rate < 0.0f)
     return fail(nullptr, TWS_ERR_INVALID, "tws_create: rain/evaporation must be >= 0");
-  if (p->backend < TWS_BACKEND_UNFUSED || p->backend > TWS_BACKEND_STREAM_TB) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown backend");
+  if (p->backend < TWS_BACKEND_UNFUSED || p->backend > TWS_BACKEND_BAND_TB) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown backend");
   if (p->boundary != TWS_BOUNDARY_REFERENCE_OPEN && p->boundary != TWS_BOUNDARY_CLOSED) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown boundary");
-  if ((p->backend == TWS_BACKEND_FUSED_TB || p->backend == TWS_BACKEND_STREAM_TB) && (p->temporal_block < 1 || p->temporal_block > TWS_MAX_TB))
+  if ((p->backend == TWS_BACKEND_FUSED_TB || is_stream_backend(p->backend)) && (p->temporal_block < 1 || p->temporal_block > TWS_MAX_TB))
     return fail(nullptr, TWS_ERR_INVALID, "tws_create: temporal_block must be 1..4");
 
   int ndev = 0;
@@ -442,7 +446,7 @@ tws_status tws_create(const tws_params* p, tws_sim** out) {
   tws_sim* s = new (std::nothrow) tws_sim;
   if (!s) return fail(nullptr, TWS_ERR_NOMEM, "tws_create: out of host memory");
   s->prm = *p;
-  s->K = (p->backend == TWS_BACKEND_FUSED_TB || p->backend == TWS_BACKEND_STREAM_TB) ? p->temporal_block : 1;
+  s->K = (p->backend == TWS_BACKEND_FUSED_TB || is_stream_backend(p->backend)) ? p->temporal_block : 1;
   if (const char* gv = getenv("TWS_GRAPHS")) s->use_graphs = gv[0] != '0';
   DeviceGuard guard(p->device);
   Geom& g = s->geom;
@@ -679,7 +683,7 @@ tws_status tws_step_host(tws_sim* s, const float* water_in, float* water_out, vo
   }
   if (!s->st_h2d) TWS_CUDA(s, cudaStreamCreateWithFlags(&s->st_h2d, cudaStreamNonBlocking));
   if (!s->st_d2h) TWS_CUDA(s, cudaStreamCreateWithFlags(&s->st_d2h, cudaStreamNonBlocking));
-  const bool stream_be = s->prm.backend == TWS_BACKEND_STREAM_TB;
+  const bool stream_be = is_stream_backend(s->prm.backend);
   tws_status r = stream_be ? ensure_tma_stream(s) : ensure_tma(s, 1);
   if (r) return r;
   // Band height: a whole number of tile rows (tile engine) / any row count (row-streaming engine),
@@ -718,7 +722,7 @@ tws_status tws_step_host(tws_sim* s, const float* water_in, float* water_out, vo
     int r0, r1; band_rows(b, &r0, &r1);
     if (water_in) TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->band_ev[2 * std::min(b + 1, nb - 1)], 0));
     const int u0 = b * band_units, u1 = std::min(units, (b + 1) * band_units);
-    if (stream_be) TWS_CUDA(s, launch_stream(1, g, s->planes, s->tma_stream[src], src, s->consts, r0, r1, s->st_main));
+    if (stream_be) TWS_CUDA(s, launch_stream(1, g, s->planes, s->tma_stream[src], src, s->consts, r0, r1, s->st_main, stream_impl(s)));
     else TWS_CUDA(s, launch_fused(1, g, s->planes, s->tma[1][src], src, s->consts, u0, u1, s->st_main));
     s->launches += 1;
     TWS_CUDA(s, cudaEventRecord(s->band_ev[2 * b + 1], s->st_main));

@@ -74,9 +74,11 @@ cudaError_t launch_fused(int K, const Geom& g, const Planes& p, const TmaSet& tm
 // Row-streaming pipeline (stream_kernels.cu): K steps over local rows [lr0, lr1) of the strip.
 cudaError_t build_tma_boxes(const Geom& g, const Planes& p, int side, int box_x, int box_y, TmaSet* out, std::string* err,
                             int l2_promotion);   // 0 none, 1 128 B, 2 256 B
+cudaError_t build_tma_rows(const Geom& g, const Planes& p, int side, int box_x, TmaSet* out, std::string* err, int l2_promotion);
 cudaError_t stream_build_tma(const Geom& g, const Planes& p, int side, TmaSet* out, std::string* err);
+// impl 0: ring kernel (one warp per row, per-row barriers); impl 1: band kernel (CTA-synchronous skewed bands).
 cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c,
-                          int lr0, int lr1, cudaStream_t st);
+                          int lr0, int lr1, cudaStream_t st, int impl);
 cudaError_t launch_unfused_update(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st);
 cudaError_t launch_unfused_apply(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st);
 

@@ -16,7 +16,8 @@ ROOT = Path(__file__).resolve().parent.parent
 GOLD = json.loads((ROOT / "tests" / "golden" / "goldens.json").read_text())
 
 BACKENDS = [("unfused", 1, 1), ("fused", 2, 1), ("tb2", 3, 2), ("tb3", 3, 3), ("tb4", 3, 4),
-            ("stream1", 4, 1), ("stream2", 4, 2), ("stream3", 4, 3), ("stream4", 4, 4)]
+            ("stream1", 4, 1), ("stream2", 4, 2), ("stream3", 4, 3), ("stream4", 4, 4),
+            ("band1", 5, 1), ("band2", 5, 2), ("band3", 5, 3), ("band4", 5, 4)]
 
 
 def bits(a):
@@ -77,7 +78,7 @@ def test_config1_dam_break_1000_steps(tws, oracle_omp, name, backend, k, rim):
             assert abs(v1 - v0) / v0 < 1e-6          # closed domain: volume conserved to 1e-6 (north_star)
 
 
-@pytest.mark.parametrize("name,backend,k", [BACKENDS[0], BACKENDS[1], BACKENDS[4], BACKENDS[6], BACKENDS[8]])
+@pytest.mark.parametrize("name,backend,k", [BACKENDS[0], BACKENDS[1], BACKENDS[4], BACKENDS[6], BACKENDS[8], BACKENDS[10], BACKENDS[12]])
 def test_config2_reference_scene_with_brush_1000_steps(tws, oracle_omp, name, backend, k):
     """BASELINE config 2: 1024x1024 reference default scene (generated ON THE GPU), brush at
     (512,512) with intensity 100/60 before every step (Scene.cpp:356-363), 1000 steps."""
@@ -327,7 +328,7 @@ def test_8192_closed_domain_conserves_volume(tws):
         assert abs(v1 - v0) / v0 < 1e-6
 
 
-@pytest.mark.parametrize("name,backend,k", [BACKENDS[0], BACKENDS[1], BACKENDS[2], BACKENDS[5], BACKENDS[8]])
+@pytest.mark.parametrize("name,backend,k", [BACKENDS[0], BACKENDS[1], BACKENDS[2], BACKENDS[5], BACKENDS[8], BACKENDS[11]])
 @pytest.mark.parametrize("W,H", [(2048, 3000), (250, 190), (37, 5), (1, 1), (4100, 1100)])
 def test_step_host_band_pipeline_matches_oracle(tws, oracle_omp, W, H, name, backend, k):
     """tws_step_host (band-pipelined upload / step / readback, several bands at 2048x3000 and

@@ -29,7 +29,7 @@ def n_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("nstrips,k,backend", [(2, 1, 2), (2, 4, 3), (3, 2, 3), (4, 3, 3), (2, 4, 4), (3, 1, 4), (4, 3, 4)])
+@pytest.mark.parametrize("nstrips,k,backend", [(2, 1, 2), (2, 4, 3), (3, 2, 3), (4, 3, 3), (2, 4, 4), (3, 1, 4), (4, 3, 4), (2, 4, 5), (3, 2, 5), (4, 3, 5)])
 @pytest.mark.parametrize("spread", [False, True], ids=["one-gpu", "multi-gpu"])
 def test_strips_in_one_process_match_whole_grid(tws, oracle_omp, nstrips, k, backend, spread):
     if spread and n_gpus() < 2:
