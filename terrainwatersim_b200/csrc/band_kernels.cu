@@ -1,0 +1,470 @@
+// band_kernels.cu — the row-streaming step in lock step ("band kernel", backend BAND_TB, sm_100a).
+//
+// Same arithmetic as every other step kernel (flowUpdate.comp:12-63 + flowApply.comp:14-53, contract in
+// cell_math.cuh / DESIGN.md section 2) and bit-identical results.  Like the ring kernel
+// (stream_kernels.cu) it blocks K whole steps over one HBM round trip by SKEWING rows in time instead
+// of recomputing halo rows: row y runs half-pass s once rows y-1 and y+1 have finished half-pass s-1.
+// The ring kernel lets every row advance on its own (per-row mbarriers); its throughput is capped by
+// the dependency cone — only NW - 2K of its NW row slots make progress per ring turn and every
+// half-pass pays a wake-up latency (ncu: a third of the warp samples sit in the neighbour waits).  The
+// band kernel runs the same schedule in lock step:
+//
+//   * a column strip (128 cells, one float4 group per lane) is marched in BANDS of R*NW rows; row
+//     o = q*NW + w of a band (q < R) belongs to warp w, which keeps its R rows in registers
+//     (24 per row) and updates them together — R independent dependency chains per thread;
+//   * half-pass s of a band updates the R*NW consecutive rows (Yb - R*NW - s, Yb - s] (Yb = last row of
+//     the band): the window slides up by one row per half-pass, which is exactly the skew the data
+//     dependency needs, so no row is ever recomputed, and a window of R*NW consecutive rows holds
+//     exactly R rows of every warp: all warps work in every half-pass and the only synchronisation is
+//     one barrier per half-pass;
+//   * rows q < R-1 and the rows q = R-1 of the warps w < NW-2K finish inside their band.  The last 2K
+//     rows of a band cannot (the rows below them are not loaded yet): their warps ("carriers") take
+//     them through NW-1-w half-passes, park them in shared memory, pick the row they parked one band
+//     earlier up again and finish that one (half-passes NW-w .. 2K);
+//   * what a vertical neighbour needs goes through one exchange slot per row (H | F+Y | F-Y, 12 B per
+//     cell); the slot of a row must outlive the band when the row below it is carried, so the last
+//     2K+1 rows of a band alternate between two slots by band parity; x neighbours are adjacent lanes;
+//   * TMA lands a warp's R rows of the NEXT band (terrain: one 2-D box per row, the five state planes:
+//     one 3-D box per row) in its private landing buffers while the current band is computed;
+//     out-of-bounds zero fill is the reference's exterior rule, as everywhere;
+//   * NGRP independent warp groups share the CTA, each with its own pieces of the (strip, row) list, its
+//     own buffers and its own named barrier: one group's barrier waits overlap the other's arithmetic.
+//
+// Rows that have nothing useful to do in a half-pass (warm-up rows above a piece, feeder rows below it
+// that are past their last needed half-pass, missing rows of the last band) are computed anyway: their
+// results are never stored (store guards) and by the schedule never reach a kept value, and computing
+// them keeps the half-pass free of per-row branches.
+#include "cell_math.cuh"
+
+namespace tws {
+
+template <int K_, int NW_, int R_, int NGRP_>
+struct BandCfg {
+  static constexpr int K = K_, NW = NW_, R = R_, NGRP = NGRP_, NT = NW_ * NGRP_ * 32;
+  static constexpr int SXW = 128;                        // one float4 group per lane
+  static constexpr int HX = stream_hx(K);
+  static constexpr int OX = SXW - 2 * HX;
+  static constexpr int HP = 2 * K;                       // computing half-passes per row
+  static constexpr int BR = R * NW;                      // rows per band
+  static constexpr int NC = HP;                          // carrier warps: NW-HP .. NW-1 (their row q = R-1)
+  static constexpr int NDB = HP + 1;                     // rows of a band with a double-buffered exchange slot
+  static constexpr int NSLOT = BR + NDB;
+  static constexpr int LAND = 6 * SXW;                   // floats per landing / parking buffer (h, d, F x4 of one row)
+  static constexpr int XROW = 3 * SXW;                   // floats per exchange slot
+  static constexpr int GROUP_FLOATS = BR * LAND + NSLOT * XROW + NC * LAND;
+  static constexpr size_t SMEM = (size_t)NGRP * GROUP_FLOATS * sizeof(float);
+  static_assert(NW >= HP + 1, "the rows of one warp-row of a band must be deeper than the dependency cone");
+  static_assert(SMEM <= 227 * 1024, "band configuration does not fit in shared memory");
+};
+
+struct BandRow {       // per-row context (the lane's column offset and store mask are shared by its rows)
+  int gy;              // global row
+  bool row_in;         // the row exists in the global grid
+  bool store;          // the row is an output row of this piece
+  size_t go;           // element offset of the lane's group in the output planes
+};
+
+// flowUpdate.comp:34-62 for the lane's 4 cells of each of its R rows.  Reads the neighbour rows' water
+// level, leaves the new outflow in registers, publishes its +-Y components; LAST also stores the flux
+// planes to HBM.  up / dn / me: 32-bit shared addresses of this lane's group in plane 0 of the slots.
+template <int R, int SXW, bool EDGE, bool LAST>
+__device__ __forceinline__ void band_flux(const uint32_t (&up)[R], const uint32_t (&dn)[R], const uint32_t (&me)[R], const float4 (&h)[R],
+                                          const float4 (&d)[R], float4 (&fx)[R], float4 (&fy)[R], float4 (&fz)[R], float4 (&fw)[R],
+                                          const BandRow (&rc)[R], const int gx, const bool st_col, const FusedOut& out, const Geom& g,
+                                          const StepConsts& c) {
+  float4 HC[R], HU[R], HD[R];
+  float HL[R], HR[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    HC[q] = add4(d[q], h[q]);                                                        // a + r, flowUpdate.comp:34
+    HU[q] = lds4(up[q]);
+    HD[q] = lds4(dn[q]);
+  }
+  // x neighbours sit in the adjacent lanes; the two strip-edge cells get a wrapped value: they lie in the
+  // x halo, whose results are never kept
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    HL[q] = __shfl_up_sync(0xffffffffu, HC[q].w, 1);
+    HR[q] = __shfl_down_sync(0xffffffffu, HC[q].x, 1);
+  }
+  float total[R][4], scale[R][4];
+  bool need = false;
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    if (!EDGE && TWS_PACKED) {
+      flux_raw4(HC[q], HU[q], HD[q], HL[q], HR[q], fx[q], fy[q], fz[q], fw[q], c, total[q]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dep = comp(d[q], i);
+        const bool over = total[q][i] > dep;                                         // :58
+        scale[q][i] = over ? 0.0f : 1.0f;
+        need = need || (over && dep != 0.0f);
+      }
+      continue;
+    }
+    float* pfx = &fx[q].x; float* pfy = &fy[q].x; float* pfz = &fz[q].x; float* pfw = &fw[q].x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float Hc = comp(HC[q], i);
+      float hxp = (i < 3) ? comp(HC[q], i + 1) : HR[q];
+      float hxm = (i > 0) ? comp(HC[q], i - 1) : HL[q];
+      float hyp = comp(HD[q], i), hym = comp(HU[q], i);
+      if (EDGE && c.closed) {
+        const int x = gx + i;
+        if (x + 1 >= g.W) hxp = Hc;
+        if (x - 1 < 0) hxm = Hc;
+        if (rc[q].gy + 1 >= g.Hg) hyp = Hc;
+        if (rc[q].gy - 1 < 0) hym = Hc;
+      }
+      total[q][i] = flux_raw(Hc, hxp, hxm, hyp, hym, pfx[i], pfy[i], pfz[i], pfw[i], c);
+      const float dep = comp(d[q], i);
+      const bool over = total[q][i] > dep;                                           // :58
+      scale[q][i] = over ? 0.0f : 1.0f;          // a == 0 -> a/total == +0 ; total <= a -> no scaling (x*1 == x)
+      need = need || (over && dep != 0.0f);
+    }
+  }
+  if (need) {                                    // the rare IEEE divisions: a wet cell that would drain completely
+#pragma unroll
+    for (int q = 0; q < R; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dep = comp(d[q], i);
+        if (total[q][i] > dep && dep != 0.0f) scale[q][i] = __fdiv_rn(dep, total[q][i]);   // :59
+      }
+  }
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    float* pfx = &fx[q].x; float* pfy = &fy[q].x; float* pfz = &fz[q].x; float* pfw = &fw[q].x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pfx[i] = __fmul_rn(pfx[i], scale[q][i]); pfy[i] = __fmul_rn(pfy[i], scale[q][i]);
+      pfz[i] = __fmul_rn(pfz[i], scale[q][i]); pfw[i] = __fmul_rn(pfw[i], scale[q][i]);
+      if (EDGE && !(rc[q].row_in && (unsigned)(gx + i) < (unsigned)g.W)) { pfx[i] = 0.f; pfy[i] = 0.f; pfz[i] = 0.f; pfw[i] = 0.f; }
+    }
+    sts4(me[q] + 4 * SXW, fz[q]);                // plane 1: +Y outflow, read by the row below
+    sts4(me[q] + 8 * SXW, fw[q]);                // plane 2: -Y outflow, read by the row above
+    if (LAST && rc[q].store && st_col && !TWS_DBG_NOSTORE) {
+      st4(out.F[0] + rc[q].go, fx[q]); st4(out.F[1] + rc[q].go, fy[q]); st4(out.F[2] + rc[q].go, fz[q]); st4(out.F[3] + rc[q].go, fw[q]);
+    }
+  }
+}
+
+// flowApply.comp:38-46 with the source/sink extension compiled in or out.
+template <bool EXT>
+__device__ __forceinline__ float band_apply_cell(float depth, float fx, float fy, float fz, float fw, float iX1, float iX0, float iY1,
+                                                 float iY0, const StepConsts& c, float& vx, float& vy) {
+  const float in = __fadd_rn(__fadd_rn(__fadd_rn(iX1, iX0), iY1), iY0);              // :38
+  const float out = __fadd_rn(__fadd_rn(__fadd_rn(fx, fy), fz), fw);                 // :39
+  float nd = max0(__fadd_rn(depth, __fmul_rn(__fsub_rn(in, out), c.area_inv)));      // :41
+  if (EXT) nd = max0(__fsub_rn(__fadd_rn(nd, c.rain_step), c.evap_step));            // EXT (same expression as apply_cell)
+  vx = __fsub_rn(__fsub_rn(iX1, fx), __fsub_rn(iX0, fy));                            // :45
+  vy = __fsub_rn(__fsub_rn(iY1, fz), __fsub_rn(iY0, fw));                            // :46
+  return nd;
+}
+
+// flowApply.comp:32-52 for the lane's 4 cells of each of its R rows.  Reads the neighbour rows' +-Y
+// outflow; not LAST: the new depth stays in registers and the new water level is published; LAST: depth
+// and the packed fp16 flow vector go to HBM.
+template <int R, int SXW, bool EDGE, bool LAST, bool EXT>
+__device__ __forceinline__ void band_depth(const uint32_t (&up)[R], const uint32_t (&dn)[R], const uint32_t (&me)[R], const float4 (&h)[R],
+                                           float4 (&d)[R], const float4 (&fx)[R], const float4 (&fy)[R], const float4 (&fz)[R],
+                                           const float4 (&fw)[R], const BandRow (&rc)[R], const int gx, const bool st_col,
+                                           const FusedOut& out, const Geom& g, const StepConsts& c) {
+  float4 iy1[R], iy0[R];
+  float l[R], r[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    iy1[q] = lds4(dn[q] + 8 * SXW);            // F(x,y+1).w, flowApply.comp:34
+    iy0[q] = lds4(up[q] + 4 * SXW);            // F(x,y-1).z, :35
+  }
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    l[q] = __shfl_up_sync(0xffffffffu, fx[q].w, 1);       // F(x-1,y).x (:33): the left cell's +X outflow
+    r[q] = __shfl_down_sync(0xffffffffu, fy[q].x, 1);     // F(x+1,y).y (:32): the right cell's -X outflow
+  }
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    float nd[4]; uint32_t nv[4];
+    if (!EDGE && TWS_PACKED) {
+      float4 nd4; uint4 nv4 = make_uint4(0u, 0u, 0u, 0u);
+      apply4<LAST>(d[q], fx[q], fy[q], fz[q], fw[q], l[q], r[q], iy1[q], iy0[q], c, EXT, nd4, nv4);
+      nd[0] = nd4.x; nd[1] = nd4.y; nd[2] = nd4.z; nd[3] = nd4.w;
+      nv[0] = nv4.x; nv[1] = nv4.y; nv[2] = nv4.z; nv[3] = nv4.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float iX1 = (i < 3) ? comp(fy[q], i + 1) : r[q];
+        const float iX0 = (i > 0) ? comp(fx[q], i - 1) : l[q];
+        float vx, vy;
+        nd[i] = band_apply_cell<EXT>(comp(d[q], i), comp(fx[q], i), comp(fy[q], i), comp(fz[q], i), comp(fw[q], i), iX1, iX0,
+                                     comp(iy1[q], i), comp(iy0[q], i), c, vx, vy);
+        if (LAST) nv[i] = pack_half2(vx, vy);
+        if (EDGE && !(rc[q].row_in && (unsigned)(gx + i) < (unsigned)g.W)) { nd[i] = 0.f; if (LAST) nv[i] = 0u; }
+      }
+    }
+    if (!LAST) {
+      d[q] = make_float4(nd[0], nd[1], nd[2], nd[3]);
+      sts4(me[q], add4(d[q], h[q]));
+    } else if (rc[q].store && st_col && !TWS_DBG_NOSTORE) {
+      st4(out.d + rc[q].go, make_float4(nd[0], nd[1], nd[2], nd[3]));
+      *reinterpret_cast<uint4*>(out.v + rc[q].go) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+    }
+  }
+}
+
+template <class C, bool EXT>
+__global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_constant__ CUtensorMap tm_h,
+                                                             const __grid_constant__ CUtensorMap tm_s,
+                                                             FusedOut out, Geom g, StepConsts c, int lr0, int lr1, int nstrips,
+                                                             int tma_y_bias) {
+  constexpr int K = C::K, NW = C::NW, R = C::R, BR = C::BR, SXW = C::SXW, HX = C::HX, OX = C::OX, HP = C::HP, LAND = C::LAND, XROW = C::XROW;
+  extern __shared__ __align__(1024) float smem[];
+  __shared__ uint64_t full_all[NW * C::NGRP];
+  // read through volatile asm: the thread index stays in a register instead of being re-read (S2R, ~20
+  // cycles of latency) and re-derived in every half-pass
+  uint32_t tid_u;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_u));
+  const int tid = (int)tid_u, lane = tid & 31, grp = (tid >> 5) / NW, warp = (tid >> 5) - grp * NW;   // warp: index inside the group
+  float* gsm = smem + grp * C::GROUP_FLOATS;              // this group's landing buffers | exchange slots | parking
+  uint64_t* full = full_all + grp * NW + warp;
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(NW * 32) : "memory"); };
+  float* land = gsm + warp * (R * LAND);                  // R landing buffers of this warp
+  const float* land_l = land + lane * 4;
+  const uint32_t xch = smem_u32(gsm + BR * LAND + lane * 4);
+  const int pw = (NW - 1 - warp) < HP ? (NW - 1 - warp) : HP;     // half-passes the last row gets inside its own band
+  const bool carrier = pw < HP;
+  float* park = gsm + BR * LAND + C::NSLOT * XROW + (carrier ? warp - (NW - C::NC) : 0) * LAND + lane * 4;
+
+  // Exchange slots.  Band row o = q*NW + warp uses slot o, except the last NDB rows of a band, which
+  // alternate between two slots by band parity.  The row above o = 0 is the last row of the previous
+  // band, the row below o = BR-1 the first row of the next one.
+  auto slot_off = [&](int o, int& dbl) {                  // byte offset of the first slot of band row o; dbl: its parity stride
+    const bool db = o >= BR - C::NDB;
+    dbl = db ? XROW * 4 : 0;
+    return (db ? (BR - C::NDB) + 2 * (o - (BR - C::NDB)) : o) * XROW * 4;
+  };
+  int sb_me[R], db_me[R], sb_up[R], db_up[R], ju[R], sb_dn[R], db_dn[R], jd[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    const int o = q * NW + warp;
+    sb_me[q] = slot_off(o, db_me[q]);
+    ju[q] = o == 0 ? -1 : 0;
+    sb_up[q] = slot_off(o == 0 ? BR - 1 : o - 1, db_up[q]);
+    jd[q] = o == BR - 1 ? 1 : 0;
+    sb_dn[q] = slot_off(o == BR - 1 ? 0 : o + 1, db_dn[q]);
+  }
+
+  if (tid == 0) {
+#pragma unroll 1
+    for (int i = 0; i < NW * C::NGRP; ++i) mbar_init(&full_all[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();                                        // the only CTA-wide barrier: the mbarriers exist
+  uint32_t parity = 0;
+
+  const long long Rows = (long long)(lr1 - lr0);
+  const long long TR = Rows * nstrips;
+  const long long vcta = (long long)blockIdx.x * C::NGRP + grp, nvcta = (long long)gridDim.x * C::NGRP;   // every group is a virtual CTA
+  const long long lin_begin = TR * vcta / nvcta, lin_end = TR * (vcta + 1) / nvcta;
+
+#pragma unroll 1
+  for (long long lin = lin_begin; lin < lin_end;) {
+    const int strip = (int)(lin / Rows);
+    const int ya = lr0 + (int)(lin - (long long)strip * Rows);
+    const int yb = (int)((long long)ya + (lin_end - lin) < (long long)lr1 ? (long long)ya + (lin_end - lin) : (long long)lr1);
+    lin += yb - ya;
+    const int sx0 = strip * OX - HX;
+    const int ystart = ya - HP;                           // 2K warm-up rows above, 2K feeder rows below
+    const int N = (yb - ya) + 2 * HP;
+    const int J = (N + BR - 1) / BR;                      // bands that load rows; band J only finishes the carried ones
+    const bool xedge = sx0 < 0 || sx0 + SXW > g.W;
+    const int gx = sx0 + lane * 4;
+    const bool st_col = lane * 4 >= HX && lane * 4 < HX + OX && gx < g.pitch;
+
+    group_sync();                                         // every warp of the group is done with the previous piece
+
+    auto issue = [&](int i0) {                            // one lane: land the warp's R rows of the band starting at piece row i0
+      if (!TWS_DBG_NOFENCE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(full, (uint32_t)(R * LAND * sizeof(float)));
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const int ty = ystart + i0 + q * NW + warp + tma_y_bias;       // rows past the piece or the grid: fetched or zero-filled, never used
+        tma_load_2d(land + q * LAND, &tm_h, sx0, ty, full);
+        tma_load_3d(land + q * LAND + SXW, &tm_s, sx0, ty, 0, full);   // d, F+X, F-X, F+Y, F-Y in one operation
+      }
+    };
+    if (lane == 0 && warp < N) issue(0);
+
+    // the rows this warp is working on: registers, row context, where they exchange with their neighbours
+    float4 h[R], d[R], fx[R], fy[R], fz[R], fw[R];
+    BandRow rc[R];
+    uint32_t x_me[R], x_up[R], x_dn[R];
+    bool plain = false;                                   // all R rows are interior rows of the global grid (no masks needed)
+    auto set_row = [&](int q, int jj, int i) {            // slot q <- piece row i of band jj
+      const int y = ystart + i;
+      rc[q].gy = g.row0 + y;
+      rc[q].row_in = (unsigned)rc[q].gy < (unsigned)g.Hg;
+      rc[q].store = y >= ya && y < yb;
+      rc[q].go = (size_t)((long long)y * g.pitch) + gx;             // only dereferenced when rc.store (y >= 0)
+      x_me[q] = keep_u32(xch + sb_me[q] + ((jj & 1) ? db_me[q] : 0));
+      x_up[q] = keep_u32(xch + sb_up[q] + (((jj + ju[q]) & 1) ? db_up[q] : 0));
+      x_dn[q] = keep_u32(xch + sb_dn[q] + (((jj + jd[q]) & 1) ? db_dn[q] : 0));
+    };
+    auto classify = [&]() {
+      bool e = xedge;
+#pragma unroll
+      for (int q = 0; q < R; ++q) e = e || rc[q].gy <= 0 || rc[q].gy >= g.Hg - 1;
+      plain = !e;
+    };
+    // park the new last row, resume the row parked one band ago (plane by plane through one temporary)
+    auto swap_rows = [&](int jj) {
+      constexpr int q = R - 1;
+      float4 t;
+      t = ld4(park);           st4(park, h[q]);            h[q] = t;
+      t = ld4(park + SXW);     st4(park + SXW, d[q]);      d[q] = t;
+      t = ld4(park + 2 * SXW); st4(park + 2 * SXW, fx[q]); fx[q] = t;
+      t = ld4(park + 3 * SXW); st4(park + 3 * SXW, fy[q]); fy[q] = t;
+      t = ld4(park + 4 * SXW); st4(park + 4 * SXW, fz[q]); fz[q] = t;
+      t = ld4(park + 5 * SXW); st4(park + 5 * SXW, fw[q]); fw[q] = t;
+      set_row(q, jj - 1, (jj - 1) * BR + q * NW + warp);            // band -1 (first swap of a piece): rows above the piece, never stored
+      classify();
+    };
+
+#pragma unroll 1
+    for (int j = 0; j <= J; ++j) {
+      const int i0 = j * BR;
+#pragma unroll
+      for (int q = 0; q < R; ++q) set_row(q, j, i0 + q * NW + warp);
+      classify();
+      // ---- half-pass 0: registers <- landing buffers; publish H; prefetch this warp's rows of the next band ----
+      if (i0 + warp < N) {
+        mbar_wait(full, parity);
+        parity ^= 1u;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          const float* lq = land_l + q * LAND;
+          h[q] = ld4(lq);            d[q] = ld4(lq + SXW);
+          fx[q] = ld4(lq + 2 * SXW); fy[q] = ld4(lq + 3 * SXW);
+          fz[q] = ld4(lq + 4 * SXW); fw[q] = ld4(lq + 5 * SXW);
+        }
+        __syncwarp();
+        if (lane == 0 && i0 + BR + warp < N) issue(i0 + BR);
+#pragma unroll
+        for (int q = 0; q < R; ++q) sts4(x_me[q], add4(d[q], h[q]));
+      }
+      group_sync();
+
+      if (!carrier && plain) {
+        // ---- the common case: interior rows that start and finish inside this band ----
+#pragma unroll 1
+        for (int lv = 1; lv < K; ++lv) {
+          band_flux<R, SXW, false, false>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+          group_sync();
+          band_depth<R, SXW, false, false, EXT>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+          group_sync();
+        }
+        band_flux<R, SXW, false, true>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+        group_sync();
+        band_depth<R, SXW, false, true, EXT>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+        group_sync();
+      } else {
+        // ---- carriers (their last row changes mid-band) and rows on the grid edge ----
+        const int swap_at = carrier ? pw + 1 : 0;
+#pragma unroll 1
+        for (int s = 1; s <= HP; ++s) {
+          if (s == swap_at) swap_rows(j);
+          const bool last = s >= HP - 1;
+          if (s & 1) {
+            if (!plain) {
+              if (last) band_flux<R, SXW, true, true>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+              else band_flux<R, SXW, true, false>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+            } else {
+              if (last) band_flux<R, SXW, false, true>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+              else band_flux<R, SXW, false, false>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+            }
+          } else {
+            if (!plain) {
+              if (last) band_depth<R, SXW, true, true, EXT>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+              else band_depth<R, SXW, true, false, EXT>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+            } else {
+              if (last) band_depth<R, SXW, false, true, EXT>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+              else band_depth<R, SXW, false, false, EXT>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+            }
+          }
+          group_sync();
+        }
+      }
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+#ifndef TWS_BAND_R
+#define TWS_BAND_R 1             // rows per warp and band
+#endif
+#ifndef TWS_BAND_NGRP
+#define TWS_BAND_NGRP 2          // independent warp groups per CTA
+#endif
+#ifndef TWS_BAND_NW
+#define TWS_BAND_NW 24           // warps per CTA (all groups)
+#endif
+// a group must be deeper than the dependency cone (2K + 1 warps): fewer groups for the larger K
+constexpr int band_groups(int K) {
+  return TWS_BAND_NW / TWS_BAND_NGRP >= 2 * K + 1 ? TWS_BAND_NGRP : (TWS_BAND_NW / 2 >= 2 * K + 1 ? 2 : 1);
+}
+template <int K> struct BandCfgFor { using type = BandCfg<K, TWS_BAND_NW / band_groups(K), TWS_BAND_R, band_groups(K)>; };
+
+static int band_sm_count() {
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!cached[dev & 63]) cudaDeviceGetAttribute(&cached[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+  return cached[dev & 63] > 0 ? cached[dev & 63] : 148;
+}
+
+template <int K, bool EXT>
+static cudaError_t launch_band_k(const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
+                                 cudaStream_t st) {
+  using C = typename BandCfgFor<K>::type;
+  if (C::SXW != stream_strip_width()) return cudaErrorInvalidValue;      // ring and band kernels share the row descriptors
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = band_step_kernel<C, EXT>;
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  if (lr1 <= lr0) return cudaSuccess;
+  const int dst = 1 - src;
+  const size_t row0_off = (size_t)TWS_HALO_ROWS * g.pitch;
+  FusedOut out;
+  out.d = p.d[dst] + row0_off;
+  for (int i = 0; i < 4; ++i) out.F[i] = p.F[dst][i] + row0_off;
+  out.v = p.v + row0_off;
+  const int nstrips = (g.W + C::OX - 1) / C::OX;
+  const long long total_rows = (long long)nstrips * (lr1 - lr0);
+  // one persistent CTA per SM; small grids: at least ~4 bands of rows per group so the 4K warm-up / feeder rows amortise
+  const long long min_rows = 4LL * C::BR * C::NGRP;
+  long long want = (total_rows + min_rows - 1) / min_rows;
+  const int sms = band_sm_count();
+  const int grid = (int)(want < 1 ? 1 : (want < sms ? want : sms));
+  const int bias = g.has_up ? TWS_HALO_ROWS : 0;
+  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], out, g, c, lr0, lr1, nstrips, bias);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_band(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
+                        cudaStream_t st) {
+  const bool ext = c.ext_sources != 0;
+  switch (K) {
+    case 1: return ext ? launch_band_k<1, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<1, false>(g, p, tma, src, c, lr0, lr1, st);
+    case 2: return ext ? launch_band_k<2, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<2, false>(g, p, tma, src, c, lr0, lr1, st);
+    case 3: return ext ? launch_band_k<3, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<3, false>(g, p, tma, src, c, lr0, lr1, st);
+    case 4: return ext ? launch_band_k<4, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<4, false>(g, p, tma, src, c, lr0, lr1, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace tws

@@ -227,6 +227,35 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
+// Shared-memory float4 access through 32-bit shared-window addresses.  The exchange-slot addresses are
+// kept as opaque 32-bit values: left as generic pointers derived from the warp index, the compiler
+// re-derives them (shared-window base, slot selects, multiplies: ~35 integer instructions) in every
+// half-pass rather than spend three registers on them.
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t keep_u32(uint32_t v) {       // pins a value in a register (no rematerialisation)
+  asm volatile("" : "+r"(v));
+  return v;
+}
+
+#ifndef TWS_STREAM_HX_MIN
+#define TWS_STREAM_HX_MIN 8    // tuning: widen the x halo so that the output columns of a strip start on a 64 / 128 B boundary
+#endif
+constexpr int stream_hx(int K) { return ((2 * K + 3) / 4) * 4 > TWS_STREAM_HX_MIN ? ((2 * K + 3) / 4) * 4 : TWS_STREAM_HX_MIN; }
+
+#ifndef TWS_DBG_NOFENCE
+#define TWS_DBG_NOFENCE 0   // tuning experiment only
+#endif
+#ifndef TWS_DBG_NOSTORE
+#define TWS_DBG_NOSTORE 0   // tuning experiment only: 1 drops the HBM stores (wrong results)
+#endif
+
 struct FusedOut {          // plane pointers at local row 0
   float* d; float* F[4]; uint32_t* v;
 };

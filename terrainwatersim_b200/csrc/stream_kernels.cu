@@ -29,11 +29,6 @@
 
 namespace tws {
 
-#ifndef TWS_STREAM_HX_MIN
-#define TWS_STREAM_HX_MIN 8    // tuning: widen the x halo so that the output columns of a strip start on a 64 / 128 B boundary
-#endif
-constexpr int stream_hx(int K) { return ((2 * K + 3) / 4) * 4 > TWS_STREAM_HX_MIN ? ((2 * K + 3) / 4) * 4 : TWS_STREAM_HX_MIN; }
-
 template <int K_, int NW_, int G_>
 struct StreamCfg {
   static constexpr int K = K_, NW = NW_, NT = NW_ * 32, G = G_;
@@ -63,12 +58,6 @@ struct StreamCfg {
 //   0 — progress words: each slot publishes `rows done * NHP + half-passes done` (st.release) and
 //     a waiting warp polls its two neighbours' words (ld.acquire, broadcast LDS).
 // ------------------------------------------------------------------------------------------
-#ifndef TWS_DBG_NOFENCE
-#define TWS_DBG_NOFENCE 0   // tuning experiment only
-#endif
-#ifndef TWS_DBG_NOSTORE
-#define TWS_DBG_NOSTORE 0   // tuning experiment only: 1 drops the HBM stores (wrong results)
-#endif
 #ifndef TWS_STREAM_WAIT
 #define TWS_STREAM_WAIT 5
 #endif
@@ -93,23 +82,6 @@ __device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t addr) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
-}
-
-// Shared-memory float4 access through 32-bit shared-window addresses.  The exchange-slot addresses are
-// kept as opaque 32-bit values: left as generic pointers derived from the warp index, the compiler
-// re-derives them (shared-window base, slot selects, multiplies: ~35 integer instructions) in every
-// half-pass rather than spend three registers on them.
-__device__ __forceinline__ float4 lds4(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts4(uint32_t a, const float4& v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ uint32_t keep_u32(uint32_t v) {       // pins a value in a register (no rematerialisation)
-  asm volatile("" : "+r"(v));
-  return v;
 }
 
 // Per-row synchronisation cursor: advanced by one half-pass per wait() / signal().
@@ -521,232 +493,6 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// Band kernel: the same row streaming, synchronised by the CTA instead of per-row barriers.
-// ------------------------------------------------------------------------------------------
-// The ring kernel above keeps NW rows in flight and lets each advance as soon as its two neighbours
-// allow; its throughput is capped by the dependency cone: only NW - 2K of the NW row slots make
-// progress per ring turn, and every half-pass pays a wake-up latency (ncu: 35 % of the warp samples
-// sit in the neighbour waits).  The band kernel runs the same skewed schedule in lock step:
-//
-//   * a column strip is marched in BANDS of NW rows, row i of the piece belongs to warp i % NW;
-//   * half-pass s of a band updates the NW consecutive rows (Yb - NW - s, Yb - s] (Yb = last row of the
-//     band): the window slides up by one row per half-pass, which is exactly the skew the data
-//     dependency needs (row y at half-pass s reads rows y-1, y+1 after half-pass s-1) — no row is ever
-//     recomputed, and a window of NW consecutive rows holds exactly one row of every warp: all warps
-//     work in every half-pass, there is nothing to wait for but the __syncthreads between half-passes;
-//   * a warp w < NW - 2K finishes its row inside the band.  The last 2K warps ("carriers") get through
-//     NW-1-w half-passes only; they park the new row in shared memory, pick the row they parked in
-//     the previous band up again and finish that one (half-passes NW-w .. 2K).  Row state lives in
-//     registers while it is worked on (24 per lane and float4 group, as in the ring kernel);
-//   * the exchange slot (H | F+Y | F-Y) of a row must outlive the band when the row below is carried,
-//     so the last 2K+1 warps alternate between two slots by band parity;
-//   * TMA lands a warp's next row (one band ahead) in its private landing buffer while the current
-//     band is computed; out-of-bounds zero fill is the reference's exterior rule, as everywhere.
-template <int K_, int NW_, int G_, int NGRP_>
-struct BandCfg {
-  // NGRP independent groups of NW warps share the CTA: each marches its own pieces with its own named
-  // barrier, so one group's barrier waits and store bursts overlap the other group's arithmetic.
-  static constexpr int K = K_, NW = NW_, NGRP = NGRP_, NT = NW_ * NGRP_ * 32, G = G_;
-  static constexpr int SXW = 128 * G;
-  static constexpr int HX = stream_hx(K);
-  static constexpr int OX = SXW - 2 * HX;
-  static constexpr int HP = 2 * K;                       // computing half-passes per row
-  static constexpr int NC = HP;                          // carrier warps: NW-HP .. NW-1
-  static constexpr int NDB = HP + 1;                     // warps with a double-buffered exchange slot
-  static constexpr int NSLOT = NW + NDB;
-  static constexpr int LAND = 6 * SXW;                   // floats per landing / parking buffer
-  static constexpr int XROW = 3 * SXW;                   // floats per exchange slot
-  static constexpr int GROUP_FLOATS = NW * LAND + NSLOT * XROW + NC * LAND;
-  static constexpr size_t SMEM = (size_t)NGRP * GROUP_FLOATS * sizeof(float);
-  static_assert(NW >= HP + 1, "a band must be deeper than the dependency cone");
-  static_assert(SMEM <= 227 * 1024, "band configuration does not fit in shared memory");
-};
-
-template <class C>
-__device__ __forceinline__ int band_slot_base(int w) {   // first exchange slot of warp w's rows
-  return w < C::NW - C::NDB ? w : (C::NW - C::NDB) + 2 * (w - (C::NW - C::NDB));
-}
-
-template <class C, bool EXT>
-__global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_constant__ CUtensorMap tm_h,
-                                                             const __grid_constant__ CUtensorMap tm_s,
-                                                             FusedOut out, Geom g, StepConsts c, int lr0, int lr1, int nstrips,
-                                                             int tma_y_bias) {
-  constexpr int K = C::K, NW = C::NW, G = C::G, SXW = C::SXW, HX = C::HX, OX = C::OX, HP = C::HP, LAND = C::LAND, XROW = C::XROW;
-  extern __shared__ __align__(1024) float smem[];
-  __shared__ uint64_t full_all[NW * C::NGRP];
-  // read through volatile asm: the thread index stays in a register instead of being re-read (S2R, ~20
-  // cycles of latency) and re-derived in every half-pass
-  uint32_t tid_u;
-  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_u));
-  const int tid = (int)tid_u, lane = tid & 31, grp = (tid >> 5) / NW, warp = (tid >> 5) - grp * NW;   // warp: index inside the group
-  float* gsm = smem + grp * C::GROUP_FLOATS;              // this group's landing buffers | exchange slots | parking
-  uint64_t* full = full_all + grp * NW;
-  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(NW * 32) : "memory"); };
-  float* land = gsm + warp * LAND;
-  const float* land_l = land + lane * 4;
-  const uint32_t xch = smem_u32(gsm + NW * LAND + lane * 4);
-  const int pw = (NW - 1 - warp) < HP ? (NW - 1 - warp) : HP;     // half-passes the new row gets inside its own band
-  const bool carrier = pw < HP;
-  float* park = gsm + NW * LAND + C::NSLOT * XROW + (carrier ? warp - (NW - C::NC) : 0) * LAND + lane * 4;
-  // exchange slots of this warp's rows and of the rows above / below them: slot = base + (band & 1 if double buffered)
-  const int wu = warp == 0 ? NW - 1 : warp - 1, ju = warp == 0 ? -1 : 0;          // the row above a warp-0 row belongs to the previous band
-  const int wd = warp == NW - 1 ? 0 : warp + 1, jd = warp == NW - 1 ? 1 : 0;      // the row below a last-warp row to the next one
-  const int sb_me = band_slot_base<C>(warp) * XROW * 4, sb_up = band_slot_base<C>(wu) * XROW * 4, sb_dn = band_slot_base<C>(wd) * XROW * 4;
-  const int db_me = warp >= NW - C::NDB ? XROW * 4 : 0, db_up = wu >= NW - C::NDB ? XROW * 4 : 0, db_dn = wd >= NW - C::NDB ? XROW * 4 : 0;
-
-  if (tid == 0) {
-#pragma unroll 1
-    for (int i = 0; i < NW * C::NGRP; ++i) mbar_init(&full_all[i], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();                                        // the only CTA-wide barrier: the mbarriers exist
-  uint32_t parity = 0;
-
-  const long long R = (long long)(lr1 - lr0);
-  const long long TR = R * nstrips;
-  const long long vcta = (long long)blockIdx.x * C::NGRP + grp, nvcta = (long long)gridDim.x * C::NGRP;   // every group is a virtual CTA
-  const long long lin_begin = TR * vcta / nvcta, lin_end = TR * (vcta + 1) / nvcta;
-
-#pragma unroll 1
-  for (long long lin = lin_begin; lin < lin_end;) {
-    const int strip = (int)(lin / R);
-    const int ya = lr0 + (int)(lin - (long long)strip * R);
-    const int yb = (int)((long long)ya + (lin_end - lin) < (long long)lr1 ? (long long)ya + (lin_end - lin) : (long long)lr1);
-    lin += yb - ya;
-    const int sx0 = strip * OX - HX;
-    const int ystart = ya - HP;                           // 2K warm-up rows above, 2K feeder rows below
-    const int N = (yb - ya) + 2 * HP;
-    const int J = (N + NW - 1) / NW;                      // bands that load rows; band J only finishes the carried ones
-    const bool xedge = sx0 < 0 || sx0 + SXW > g.W;
-
-    group_sync();                                         // every warp of the group is done with the previous piece
-
-    auto issue = [&](int y) {                             // one lane: land row y in this warp's buffer
-      if (!TWS_DBG_NOFENCE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&full[warp], (uint32_t)(LAND * sizeof(float)));
-      const int ty = y + tma_y_bias;
-      tma_load_2d(land, &tm_h, sx0, ty, &full[warp]);
-
-      tma_load_3d(land + SXW, &tm_s, sx0, ty, 0, &full[warp]);     // d, F+X, F-X, F+Y, F-Y in one operation
-    };
-    if (lane == 0 && warp < N) issue(ystart + warp);
-
-    RowCtx<G> rc;
-#pragma unroll
-    for (int q = 0; q < G; ++q) {
-      const int o = (lane + 32 * q) * 4;
-      rc.gx[q] = sx0 + o;
-      rc.st[q] = o >= HX && o < HX + OX && rc.gx[q] < g.pitch;
-    }
-
-    // the row this warp is working on: registers + where it exchanges with its neighbours
-    float4 h[G], d[G], fx[G], fy[G], fz[G], fw[G];
-    bool valid = false, plain = false;                    // plain: interior row that runs all 2K half-passes
-    int smax = 0;
-    uint32_t x_me = xch, x_up = xch, x_dn = xch;
-    auto set_row = [&](int jj, int i) {                   // piece row i of band jj (i < 0 or >= N: no row)
-      valid = i >= 0 && i < N;
-      const int y = ystart + i;
-      rc.gy = g.row0 + y;
-      rc.row_in = (unsigned)rc.gy < (unsigned)g.Hg;
-      rc.store = y >= ya && y < yb;
-      const size_t rowoff = (size_t)((long long)y * g.pitch);      // only dereferenced when rc.store (y >= 0)
-#pragma unroll
-      for (int q = 0; q < G; ++q) rc.go[q] = rowoff + rc.gx[q];
-      // rows below the piece only feed the rows above them: row yb-1+m stops after half-pass 2K-m
-      smax = (y < yb) ? HP : HP - (y - yb + 1);
-      plain = !(xedge || rc.gy <= 0 || rc.gy >= g.Hg - 1) && smax == HP;
-      x_me = keep_u32(xch + sb_me + ((jj & 1) ? db_me : 0));
-      x_up = keep_u32(xch + sb_up + (((jj + ju) & 1) ? db_up : 0));
-      x_dn = keep_u32(xch + sb_dn + (((jj + jd) & 1) ? db_dn : 0));
-    };
-    // park the new row, resume the row parked one band ago (plane by plane through one temporary)
-    auto swap_rows = [&](int jj, bool hasB) {
-      const int iA = (jj - 1) * NW + warp;
-#pragma unroll
-      for (int q = 0; q < G; ++q) {
-        float* pk = park + 128 * q;
-        float4 t;
-        t = ld4(pk);           if (hasB) st4(pk, h[q]);            h[q] = t;
-        t = ld4(pk + SXW);     if (hasB) st4(pk + SXW, d[q]);      d[q] = t;
-        t = ld4(pk + 2 * SXW); if (hasB) st4(pk + 2 * SXW, fx[q]); fx[q] = t;
-        t = ld4(pk + 3 * SXW); if (hasB) st4(pk + 3 * SXW, fy[q]); fy[q] = t;
-        t = ld4(pk + 4 * SXW); if (hasB) st4(pk + 4 * SXW, fz[q]); fz[q] = t;
-        t = ld4(pk + 5 * SXW); if (hasB) st4(pk + 5 * SXW, fw[q]); fw[q] = t;
-      }
-      set_row(jj - 1, (jj > 0 && iA < N) ? iA : -1);
-    };
-
-#pragma unroll 1
-    for (int j = 0; j <= J; ++j) {
-      const int iB = j * NW + warp;
-      const bool hasB = iB < N;
-      set_row(j, iB);
-      // ---- half-pass 0: registers <- landing buffer; publish H; prefetch this warp's row of the next band ----
-      if (hasB) {
-        mbar_wait(&full[warp], parity);
-        parity ^= 1u;
-#pragma unroll
-        for (int q = 0; q < G; ++q) {
-          h[q] = ld4(land_l + 128 * q);            d[q] = ld4(land_l + SXW + 128 * q);
-          fx[q] = ld4(land_l + 2 * SXW + 128 * q); fy[q] = ld4(land_l + 3 * SXW + 128 * q);
-          fz[q] = ld4(land_l + 4 * SXW + 128 * q); fw[q] = ld4(land_l + 5 * SXW + 128 * q);
-        }
-        __syncwarp();
-        if (lane == 0 && iB + NW < N) issue(ystart + iB + NW);
-#pragma unroll
-        for (int q = 0; q < G; ++q) sts4(x_me + 512 * q, add4(d[q], h[q]));
-      }
-      group_sync();
-
-      if (!carrier && plain && valid) {
-        // ---- the common case: an interior row that starts and finishes inside this band ----
-#pragma unroll 1
-        for (int lv = 1; lv < K; ++lv) {
-          stream_flux<G, SXW, false, false>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
-          group_sync();
-          stream_depth<G, SXW, false, false, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
-          group_sync();
-        }
-        stream_flux<G, SXW, false, true>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
-        group_sync();
-        stream_depth<G, SXW, false, true, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
-        group_sync();
-      } else {
-        // ---- carriers (two rows per band), rows on the grid edge, feeder rows that stop early, no row at all ----
-        const int swap_at = carrier ? pw + 1 : 0;
-#pragma unroll 1
-        for (int s = 1; s <= HP; ++s) {
-          if (s == swap_at) swap_rows(j, hasB);
-          if (valid && s <= smax) {
-            const bool last = s >= HP - 1;
-            if (s & 1) {
-              if (!plain) {
-                if (last) stream_flux<G, SXW, true, true>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
-                else stream_flux<G, SXW, true, false>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
-              } else {
-                if (last) stream_flux<G, SXW, false, true>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
-                else stream_flux<G, SXW, false, false>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
-              }
-            } else {
-              if (!plain) {
-                if (last) stream_depth<G, SXW, true, true, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
-                else stream_depth<G, SXW, true, false, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
-              } else {
-                if (last) stream_depth<G, SXW, false, true, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
-                else stream_depth<G, SXW, false, false, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
-              }
-            }
-          }
-          group_sync();
-        }
-      }
-    }
-  }
-}
-
 // ---- host side ---------------------------------------------------------------------------
 #ifndef TWS_STREAM_G
 #define TWS_STREAM_G 1           // float4 groups per lane: rows of 128 * G cells
@@ -755,6 +501,8 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
 #define TWS_STREAM_NW (24 / TWS_STREAM_G)     // row slots (warps) per SM: 24 x 80 registers keeps the row state spill-free
 #endif
 template <int K> struct StreamCfgFor { using type = StreamCfg<K, TWS_STREAM_NW, TWS_STREAM_G>; };
+
+int stream_strip_width() { return StreamCfgFor<1>::type::SXW; }
 
 static int stream_sm_count() {
   static int cached[64] = {};
@@ -796,63 +544,11 @@ static cudaError_t launch_stream_k(const Geom& g, const Planes& p, const TmaSet&
   return cudaGetLastError();
 }
 
-#ifndef TWS_BAND_G
-#define TWS_BAND_G 1
-#endif
-#ifndef TWS_BAND_NW
-#define TWS_BAND_NW (24 / TWS_BAND_G)
-#endif
-#ifndef TWS_BAND_NGRP
-#define TWS_BAND_NGRP 2
-#endif
-template <int K> struct BandCfgFor { using type = BandCfg<K, TWS_BAND_NW / TWS_BAND_NGRP, TWS_BAND_G, TWS_BAND_NGRP>; };
-static_assert(BandCfgFor<1>::type::SXW == StreamCfgFor<1>::type::SXW, "ring and band kernels share the row descriptors");
-
-template <int K, bool EXT>
-static cudaError_t launch_band_k(const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
-                                 cudaStream_t st) {
-  using C = typename BandCfgFor<K>::type;
-  static bool attr_set[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  auto kern = band_step_kernel<C, EXT>;
-  if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return e;
-    attr_set[dev & 63] = true;
-  }
-  if (lr1 <= lr0) return cudaSuccess;
-  const int dst = 1 - src;
-  const size_t row0_off = (size_t)TWS_HALO_ROWS * g.pitch;
-  FusedOut out;
-  out.d = p.d[dst] + row0_off;
-  for (int i = 0; i < 4; ++i) out.F[i] = p.F[dst][i] + row0_off;
-  out.v = p.v + row0_off;
-  const int nstrips = (g.W + C::OX - 1) / C::OX;
-  const long long total_rows = (long long)nstrips * (lr1 - lr0);
-  // one persistent CTA per SM; small grids: at least ~4 bands of rows per CTA so the 4K warm-up / feeder rows amortise
-  const long long min_rows = 4 * C::NW * C::NGRP;
-  long long want = (total_rows + min_rows - 1) / min_rows;
-  const int sms = stream_sm_count();
-  const int grid = (int)(want < 1 ? 1 : (want < sms ? want : sms));
-  const int bias = g.has_up ? TWS_HALO_ROWS : 0;
-  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], out, g, c, lr0, lr1, nstrips, bias);
-  return cudaGetLastError();
-}
-
 // impl: 0 = ring kernel (per-row barriers), 1 = band kernel (CTA-synchronous bands)
 cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
                           cudaStream_t st, int impl) {
   const bool ext = c.ext_sources != 0;
-  if (impl == 1) {
-    switch (K) {
-      case 1: return ext ? launch_band_k<1, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<1, false>(g, p, tma, src, c, lr0, lr1, st);
-      case 2: return ext ? launch_band_k<2, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<2, false>(g, p, tma, src, c, lr0, lr1, st);
-      case 3: return ext ? launch_band_k<3, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<3, false>(g, p, tma, src, c, lr0, lr1, st);
-      case 4: return ext ? launch_band_k<4, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<4, false>(g, p, tma, src, c, lr0, lr1, st);
-      default: return cudaErrorInvalidValue;
-    }
-  }
+  if (impl == 1) return launch_band(K, g, p, tma, src, c, lr0, lr1, st);
   switch (K) {
     case 1: return ext ? launch_stream_k<1, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<1, false>(g, p, tma, src, c, lr0, lr1, st);
     case 2: return ext ? launch_stream_k<2, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<2, false>(g, p, tma, src, c, lr0, lr1, st);

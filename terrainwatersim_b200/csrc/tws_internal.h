@@ -79,6 +79,10 @@ cudaError_t stream_build_tma(const Geom& g, const Planes& p, int side, TmaSet* o
 // impl 0: ring kernel (one warp per row, per-row barriers); impl 1: band kernel (CTA-synchronous skewed bands).
 cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c,
                           int lr0, int lr1, cudaStream_t st, int impl);
+// Band kernel (band_kernels.cu): the streaming schedule in lock step; same row descriptors as the ring kernel.
+cudaError_t launch_band(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c,
+                        int lr0, int lr1, cudaStream_t st);
+int stream_strip_width();
 cudaError_t launch_unfused_update(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st);
 cudaError_t launch_unfused_apply(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st);
 
