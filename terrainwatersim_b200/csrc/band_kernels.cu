@@ -64,22 +64,62 @@ struct BandRow {       // per-row context (the lane's column offset and store ma
   size_t go;           // element offset of the lane's group in the output planes
 };
 
+// Split-phase group barrier: one mbarrier per warp group, one arrival per warp.  arrive() right after a
+// half-pass has published what the neighbour rows need, wait() right before the next half-pass reads
+// what the neighbours published — the arithmetic that needs no neighbour data (own-row sums and
+// products before the wait, scaling of the unpublished components and the HBM stores after the arrive)
+// runs while the other warps catch up.  Every warp alternates arrive / wait strictly, so a single
+// barrier and one phase bit per thread suffice (nobody can arrive for phase n+1 before it has seen
+// phase n complete).  TWS_BAND_SPLIT 0 degrades it to a plain barrier (arrive + wait back to back).
+#ifndef TWS_BAND_SPLIT
+#define TWS_BAND_SPLIT 1
+#endif
+struct GroupSync {
+  uint32_t bar;        // shared address of the group's mbarrier
+  uint32_t phase;      // parity of the phase the next wait() waits for
+  __device__ __forceinline__ void arrive() {
+    __syncwarp();                                         // every lane's shared-memory stores are ordered before the release
+    asm volatile(
+        "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\n@p mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n}" ::"r"(bar) : "memory");
+    if (!TWS_BAND_SPLIT) wait_now();
+  }
+  __device__ __forceinline__ void wait() { if (TWS_BAND_SPLIT) wait_now(); }
+  __device__ __forceinline__ void wait_now() {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
+        "TWS_GS_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TWS_GS_DONE;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.gt.u32 q, n, 16777216;\n"
+        "@q trap;\n"                                      // a barrier that never completes is a bug; a trap beats a hung GPU
+        "bra TWS_GS_LOOP;\n"
+        "TWS_GS_DONE:\n"
+        "}\n" ::"r"(bar), "r"(phase) : "memory");
+    phase ^= 1u;
+  }
+};
+
 // flowUpdate.comp:34-62 for the lane's 4 cells of each of its R rows.  Reads the neighbour rows' water
 // level, leaves the new outflow in registers, publishes its +-Y components; LAST also stores the flux
 // planes to HBM.  up / dn / me: 32-bit shared addresses of this lane's group in plane 0 of the slots.
+// Interior rows (!EDGE) are split around the barrier: the +-X outflow and the friction products need
+// only the row itself and are computed before the wait; the x components are scaled and the HBM stores
+// issued after the arrive.  Operation order per value is that of flux_raw4 / flux_raw (cell_math.cuh).
 template <int R, int SXW, bool EDGE, bool LAST>
-__device__ __forceinline__ void band_flux(const uint32_t (&up)[R], const uint32_t (&dn)[R], const uint32_t (&me)[R], const float4 (&h)[R],
-                                          const float4 (&d)[R], float4 (&fx)[R], float4 (&fy)[R], float4 (&fz)[R], float4 (&fw)[R],
-                                          const BandRow (&rc)[R], const int gx, const bool st_col, const FusedOut& out, const Geom& g,
-                                          const StepConsts& c) {
+__device__ __forceinline__ void band_flux(GroupSync& sy, const uint32_t (&up)[R], const uint32_t (&dn)[R], const uint32_t (&me)[R],
+                                          const float4 (&h)[R], const float4 (&d)[R], float4 (&fx)[R], float4 (&fy)[R], float4 (&fz)[R],
+                                          float4 (&fw)[R], const BandRow (&rc)[R], const int gx, const bool st_col, const FusedOut& out,
+                                          const Geom& g, const StepConsts& c) {
   float4 HC[R], HU[R], HD[R];
   float HL[R], HR[R];
+  float total[R][4], scale[R][4];
+  bool need = false;
 #pragma unroll
-  for (int q = 0; q < R; ++q) {
-    HC[q] = add4(d[q], h[q]);                                                        // a + r, flowUpdate.comp:34
-    HU[q] = lds4(up[q]);
-    HD[q] = lds4(dn[q]);
-  }
+  for (int q = 0; q < R; ++q) HC[q] = add4(d[q], h[q]);                              // a + r, flowUpdate.comp:34
   // x neighbours sit in the adjacent lanes; the two strip-edge cells get a wrapped value: they lie in the
   // x halo, whose results are never kept
 #pragma unroll
@@ -87,40 +127,79 @@ __device__ __forceinline__ void band_flux(const uint32_t (&up)[R], const uint32_
     HL[q] = __shfl_up_sync(0xffffffffu, HC[q].w, 1);
     HR[q] = __shfl_down_sync(0xffffffffu, HC[q].x, 1);
   }
-  float total[R][4], scale[R][4];
-  bool need = false;
+  if (!EDGE && TWS_PACKED) {
+    const f2 PHI = pk(c.friction, c.friction), ALPHA = pk(c.accel, c.accel), KAPPA = pk(c.area_inv, c.area_inv);
+    float4 tz[R], tw[R];
+    f2 sxy_lo[R], sxy_hi[R];
+    // ---- before the wait: +-X outflow (:44-45, :53-54), friction products of +-Y, fx + fy ----
 #pragma unroll
-  for (int q = 0; q < R; ++q) {
-    if (!EDGE && TWS_PACKED) {
-      flux_raw4(HC[q], HU[q], HD[q], HL[q], HR[q], fx[q], fy[q], fz[q], fw[q], c, total[q]);
+    for (int q = 0; q < R; ++q) {
+      const float Dm = __fsub_rn(HL[q], HC[q].x);
+      const float D0 = __fsub_rn(HC[q].x, HC[q].y), D1 = __fsub_rn(HC[q].y, HC[q].z), D2 = __fsub_rn(HC[q].z, HC[q].w),
+                  D3 = __fsub_rn(HC[q].w, HR[q]);
+      const float Pm = __fmul_rn(Dm, c.accel);
+      float P0, P1, P2, P3;
+      upk(mul2(pk(D0, D1), ALPHA), P0, P1);
+      upk(mul2(pk(D2, D3), ALPHA), P2, P3);
+      const float4 tx = cat4(mul2(lo2(fx[q]), PHI), mul2(hi2(fx[q]), PHI));
+      const float4 ty = cat4(mul2(lo2(fy[q]), PHI), mul2(hi2(fy[q]), PHI));
+      tz[q] = cat4(mul2(lo2(fz[q]), PHI), mul2(hi2(fz[q]), PHI));
+      tw[q] = cat4(mul2(lo2(fw[q]), PHI), mul2(hi2(fw[q]), PHI));
+      fx[q].x = max0(__fadd_rn(tx.x, P0)); fx[q].y = max0(__fadd_rn(tx.y, P1)); fx[q].z = max0(__fadd_rn(tx.z, P2)); fx[q].w = max0(__fadd_rn(tx.w, P3));
+      fy[q].x = max0(__fsub_rn(ty.x, Pm)); fy[q].y = max0(__fsub_rn(ty.y, P0)); fy[q].z = max0(__fsub_rn(ty.z, P1)); fy[q].w = max0(__fsub_rn(ty.w, P2));
+      sxy_lo[q] = add2(lo2(fx[q]), lo2(fy[q]));
+      sxy_hi[q] = add2(hi2(fx[q]), hi2(fy[q]));
+    }
+    sy.wait();                                   // the rows above and below have published their water level
+#pragma unroll
+    for (int q = 0; q < R; ++q) { HU[q] = lds4(up[q]); HD[q] = lds4(dn[q]); }
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      float Z0, Z1, Z2, Z3, W0, W1, W2, W3;
+      upk(mul2(sub2(lo2(HC[q]), lo2(HD[q])), ALPHA), Z0, Z1);                        // +Y, :46
+      upk(mul2(sub2(hi2(HC[q]), hi2(HD[q])), ALPHA), Z2, Z3);
+      upk(mul2(sub2(lo2(HC[q]), lo2(HU[q])), ALPHA), W0, W1);                        // -Y, :47
+      upk(mul2(sub2(hi2(HC[q]), hi2(HU[q])), ALPHA), W2, W3);
+      fz[q].x = max0(__fadd_rn(tz[q].x, Z0)); fz[q].y = max0(__fadd_rn(tz[q].y, Z1)); fz[q].z = max0(__fadd_rn(tz[q].z, Z2)); fz[q].w = max0(__fadd_rn(tz[q].w, Z3));
+      fw[q].x = max0(__fadd_rn(tw[q].x, W0)); fw[q].y = max0(__fadd_rn(tw[q].y, W1)); fw[q].z = max0(__fadd_rn(tw[q].z, W2)); fw[q].w = max0(__fadd_rn(tw[q].w, W3));
+      const f2 slo = add2(add2(sxy_lo[q], lo2(fz[q])), lo2(fw[q]));                  // ((fx + fy) + fz) + fw, :57
+      const f2 shi = add2(add2(sxy_hi[q], hi2(fz[q])), hi2(fw[q]));
+      upk(mul2(slo, KAPPA), total[q][0], total[q][1]);
+      upk(mul2(shi, KAPPA), total[q][2], total[q][3]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
+        const float dep = comp(d[q], i);
+        const bool over = total[q][i] > dep;                                         // :58
+        scale[q][i] = over ? 0.0f : 1.0f;        // a == 0 -> a/total == +0 ; total <= a -> no scaling (x*1 == x)
+        need = need || (over && dep != 0.0f);
+      }
+    }
+  } else {
+    sy.wait();
+#pragma unroll
+    for (int q = 0; q < R; ++q) { HU[q] = lds4(up[q]); HD[q] = lds4(dn[q]); }
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      float* pfx = &fx[q].x; float* pfy = &fy[q].x; float* pfz = &fz[q].x; float* pfw = &fw[q].x;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float Hc = comp(HC[q], i);
+        float hxp = (i < 3) ? comp(HC[q], i + 1) : HR[q];
+        float hxm = (i > 0) ? comp(HC[q], i - 1) : HL[q];
+        float hyp = comp(HD[q], i), hym = comp(HU[q], i);
+        if (EDGE && c.closed) {
+          const int x = gx + i;
+          if (x + 1 >= g.W) hxp = Hc;
+          if (x - 1 < 0) hxm = Hc;
+          if (rc[q].gy + 1 >= g.Hg) hyp = Hc;
+          if (rc[q].gy - 1 < 0) hym = Hc;
+        }
+        total[q][i] = flux_raw(Hc, hxp, hxm, hyp, hym, pfx[i], pfy[i], pfz[i], pfw[i], c);
         const float dep = comp(d[q], i);
         const bool over = total[q][i] > dep;                                         // :58
         scale[q][i] = over ? 0.0f : 1.0f;
         need = need || (over && dep != 0.0f);
       }
-      continue;
-    }
-    float* pfx = &fx[q].x; float* pfy = &fy[q].x; float* pfz = &fz[q].x; float* pfw = &fw[q].x;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float Hc = comp(HC[q], i);
-      float hxp = (i < 3) ? comp(HC[q], i + 1) : HR[q];
-      float hxm = (i > 0) ? comp(HC[q], i - 1) : HL[q];
-      float hyp = comp(HD[q], i), hym = comp(HU[q], i);
-      if (EDGE && c.closed) {
-        const int x = gx + i;
-        if (x + 1 >= g.W) hxp = Hc;
-        if (x - 1 < 0) hxm = Hc;
-        if (rc[q].gy + 1 >= g.Hg) hyp = Hc;
-        if (rc[q].gy - 1 < 0) hym = Hc;
-      }
-      total[q][i] = flux_raw(Hc, hxp, hxm, hyp, hym, pfx[i], pfy[i], pfz[i], pfw[i], c);
-      const float dep = comp(d[q], i);
-      const bool over = total[q][i] > dep;                                           // :58
-      scale[q][i] = over ? 0.0f : 1.0f;          // a == 0 -> a/total == +0 ; total <= a -> no scaling (x*1 == x)
-      need = need || (over && dep != 0.0f);
     }
   }
   if (need) {                                    // the rare IEEE divisions: a wet cell that would drain completely
@@ -132,17 +211,27 @@ __device__ __forceinline__ void band_flux(const uint32_t (&up)[R], const uint32_
         if (total[q][i] > dep && dep != 0.0f) scale[q][i] = __fdiv_rn(dep, total[q][i]);   // :59
       }
   }
+  // ---- scale and publish +-Y first: that is all the neighbour rows wait for ----
 #pragma unroll
   for (int q = 0; q < R; ++q) {
-    float* pfx = &fx[q].x; float* pfy = &fy[q].x; float* pfz = &fz[q].x; float* pfw = &fw[q].x;
+    float* pfz = &fz[q].x; float* pfw = &fw[q].x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      pfx[i] = __fmul_rn(pfx[i], scale[q][i]); pfy[i] = __fmul_rn(pfy[i], scale[q][i]);
       pfz[i] = __fmul_rn(pfz[i], scale[q][i]); pfw[i] = __fmul_rn(pfw[i], scale[q][i]);
-      if (EDGE && !(rc[q].row_in && (unsigned)(gx + i) < (unsigned)g.W)) { pfx[i] = 0.f; pfy[i] = 0.f; pfz[i] = 0.f; pfw[i] = 0.f; }
+      if (EDGE && !(rc[q].row_in && (unsigned)(gx + i) < (unsigned)g.W)) { pfz[i] = 0.f; pfw[i] = 0.f; }
     }
     sts4(me[q] + 4 * SXW, fz[q]);                // plane 1: +Y outflow, read by the row below
     sts4(me[q] + 8 * SXW, fw[q]);                // plane 2: -Y outflow, read by the row above
+  }
+  sy.arrive();
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    float* pfx = &fx[q].x; float* pfy = &fy[q].x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pfx[i] = __fmul_rn(pfx[i], scale[q][i]); pfy[i] = __fmul_rn(pfy[i], scale[q][i]);
+      if (EDGE && !(rc[q].row_in && (unsigned)(gx + i) < (unsigned)g.W)) { pfx[i] = 0.f; pfy[i] = 0.f; }
+    }
     if (LAST && rc[q].store && st_col && !TWS_DBG_NOSTORE) {
       st4(out.F[0] + rc[q].go, fx[q]); st4(out.F[1] + rc[q].go, fy[q]); st4(out.F[2] + rc[q].go, fz[q]); st4(out.F[3] + rc[q].go, fw[q]);
     }
@@ -164,51 +253,114 @@ __device__ __forceinline__ float band_apply_cell(float depth, float fx, float fy
 
 // flowApply.comp:32-52 for the lane's 4 cells of each of its R rows.  Reads the neighbour rows' +-Y
 // outflow; not LAST: the new depth stays in registers and the new water level is published; LAST: depth
-// and the packed fp16 flow vector go to HBM.
+// and the packed fp16 flow vector go to HBM.  Interior rows: the x inflow, the outflow sum and the x
+// flow component are computed before the wait; operation order per value is that of apply4.
 template <int R, int SXW, bool EDGE, bool LAST, bool EXT>
-__device__ __forceinline__ void band_depth(const uint32_t (&up)[R], const uint32_t (&dn)[R], const uint32_t (&me)[R], const float4 (&h)[R],
-                                           float4 (&d)[R], const float4 (&fx)[R], const float4 (&fy)[R], const float4 (&fz)[R],
-                                           const float4 (&fw)[R], const BandRow (&rc)[R], const int gx, const bool st_col,
-                                           const FusedOut& out, const Geom& g, const StepConsts& c) {
+__device__ __forceinline__ void band_depth(GroupSync& sy, const uint32_t (&up)[R], const uint32_t (&dn)[R], const uint32_t (&me)[R],
+                                           const float4 (&h)[R], float4 (&d)[R], const float4 (&fx)[R], const float4 (&fy)[R],
+                                           const float4 (&fz)[R], const float4 (&fw)[R], const BandRow (&rc)[R], const int gx,
+                                           const bool st_col, const FusedOut& out, const Geom& g, const StepConsts& c) {
   float4 iy1[R], iy0[R];
   float l[R], r[R];
-#pragma unroll
-  for (int q = 0; q < R; ++q) {
-    iy1[q] = lds4(dn[q] + 8 * SXW);            // F(x,y+1).w, flowApply.comp:34
-    iy0[q] = lds4(up[q] + 4 * SXW);            // F(x,y-1).z, :35
-  }
 #pragma unroll
   for (int q = 0; q < R; ++q) {
     l[q] = __shfl_up_sync(0xffffffffu, fx[q].w, 1);       // F(x-1,y).x (:33): the left cell's +X outflow
     r[q] = __shfl_down_sync(0xffffffffu, fy[q].x, 1);     // F(x+1,y).y (:32): the right cell's -X outflow
   }
+  if (!EDGE && TWS_PACKED) {
+    const f2 KAPPA = pk(c.area_inv, c.area_inv);
+    f2 ax_lo[R], ax_hi[R], out_lo[R], out_hi[R];
+    float vx[R][4];
 #pragma unroll
-  for (int q = 0; q < R; ++q) {
-    float nd[4]; uint32_t nv[4];
-    if (!EDGE && TWS_PACKED) {
-      float4 nd4; uint4 nv4 = make_uint4(0u, 0u, 0u, 0u);
-      apply4<LAST>(d[q], fx[q], fy[q], fz[q], fw[q], l[q], r[q], iy1[q], iy0[q], c, EXT, nd4, nv4);
-      nd[0] = nd4.x; nd[1] = nd4.y; nd[2] = nd4.z; nd[3] = nd4.w;
-      nv[0] = nv4.x; nv[1] = nv4.y; nv[2] = nv4.z; nv[3] = nv4.w;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float iX1 = (i < 3) ? comp(fy[q], i + 1) : r[q];
-        const float iX0 = (i > 0) ? comp(fx[q], i - 1) : l[q];
-        float vx, vy;
-        nd[i] = band_apply_cell<EXT>(comp(d[q], i), comp(fx[q], i), comp(fy[q], i), comp(fz[q], i), comp(fw[q], i), iX1, iX0,
-                                     comp(iy1[q], i), comp(iy0[q], i), c, vx, vy);
-        if (LAST) nv[i] = pack_half2(vx, vy);
-        if (EDGE && !(rc[q].row_in && (unsigned)(gx + i) < (unsigned)g.W)) { nd[i] = 0.f; if (LAST) nv[i] = 0u; }
+    for (int q = 0; q < R; ++q) {
+      // iX1 + iX0 = F(x+1,y).y + F(x-1,y).x (:38): neighbours inside the group are misaligned pairs -> scalar
+      const float a0 = __fadd_rn(fy[q].y, l[q]), a1 = __fadd_rn(fy[q].z, fx[q].x), a2 = __fadd_rn(fy[q].w, fx[q].y), a3 = __fadd_rn(r[q], fx[q].z);
+      ax_lo[q] = pk(a0, a1); ax_hi[q] = pk(a2, a3);
+      out_lo[q] = add2(add2(add2(lo2(fx[q]), lo2(fy[q])), lo2(fz[q])), lo2(fw[q]));  // :39
+      out_hi[q] = add2(add2(add2(hi2(fx[q]), hi2(fy[q])), hi2(fz[q])), hi2(fw[q]));
+      if (LAST) {                                                                     // vx = (iX1 - fx) - (iX0 - fy), :45
+        const float b0 = __fsub_rn(fy[q].y, fx[q].x), b1 = __fsub_rn(fy[q].z, fx[q].y), b2 = __fsub_rn(fy[q].w, fx[q].z), b3 = __fsub_rn(r[q], fx[q].w);
+        const float c0 = __fsub_rn(l[q], fy[q].x), c1 = __fsub_rn(fx[q].x, fy[q].y), c2 = __fsub_rn(fx[q].y, fy[q].z), c3 = __fsub_rn(fx[q].z, fy[q].w);
+        upk(sub2(pk(b0, b1), pk(c0, c1)), vx[q][0], vx[q][1]);
+        upk(sub2(pk(b2, b3), pk(c2, c3)), vx[q][2], vx[q][3]);
       }
     }
-    if (!LAST) {
-      d[q] = make_float4(nd[0], nd[1], nd[2], nd[3]);
-      sts4(me[q], add4(d[q], h[q]));
-    } else if (rc[q].store && st_col && !TWS_DBG_NOSTORE) {
-      st4(out.d + rc[q].go, make_float4(nd[0], nd[1], nd[2], nd[3]));
-      *reinterpret_cast<uint4*>(out.v + rc[q].go) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+    sy.wait();                                   // the rows above and below have published their +-Y outflow
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      iy1[q] = lds4(dn[q] + 8 * SXW);            // F(x,y+1).w, flowApply.comp:34
+      iy0[q] = lds4(up[q] + 4 * SXW);            // F(x,y-1).z, :35
     }
+    float4 nd[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const f2 inlo = add2(add2(ax_lo[q], lo2(iy1[q])), lo2(iy0[q]));                // :38
+      const f2 inhi = add2(add2(ax_hi[q], hi2(iy1[q])), hi2(iy0[q]));
+      float q0, q1, q2, q3;
+      upk(mul2(sub2(inlo, out_lo[q]), KAPPA), q0, q1);
+      upk(mul2(sub2(inhi, out_hi[q]), KAPPA), q2, q3);
+      nd[q].x = max0(__fadd_rn(d[q].x, q0)); nd[q].y = max0(__fadd_rn(d[q].y, q1));  // :41
+      nd[q].z = max0(__fadd_rn(d[q].z, q2)); nd[q].w = max0(__fadd_rn(d[q].w, q3));
+      if (EXT) {                                                                      // EXT (same expression as apply_cell)
+        const f2 RAIN = pk(c.rain_step, c.rain_step), EVAP = pk(c.evap_step, c.evap_step);
+        float e0, e1, e2, e3;
+        upk(sub2(add2(lo2(nd[q]), RAIN), EVAP), e0, e1);
+        upk(sub2(add2(hi2(nd[q]), RAIN), EVAP), e2, e3);
+        nd[q] = make_float4(max0(e0), max0(e1), max0(e2), max0(e3));
+      }
+      if (!LAST) {
+        d[q] = nd[q];
+        sts4(me[q], add4(d[q], h[q]));
+      }
+    }
+    sy.arrive();
+    if (LAST) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        float vy0, vy1, vy2, vy3;                                                     // vy = (iY1 - fz) - (iY0 - fw), :46
+        upk(sub2(sub2(lo2(iy1[q]), lo2(fz[q])), sub2(lo2(iy0[q]), lo2(fw[q]))), vy0, vy1);
+        upk(sub2(sub2(hi2(iy1[q]), hi2(fz[q])), sub2(hi2(iy0[q]), hi2(fw[q]))), vy2, vy3);
+        if (rc[q].store && st_col && !TWS_DBG_NOSTORE) {
+          st4(out.d + rc[q].go, nd[q]);
+          *reinterpret_cast<uint4*>(out.v + rc[q].go) =
+              make_uint4(pack_half2(vx[q][0], vy0), pack_half2(vx[q][1], vy1), pack_half2(vx[q][2], vy2), pack_half2(vx[q][3], vy3));
+        }
+      }
+    }
+    return;
+  }
+  sy.wait();
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    iy1[q] = lds4(dn[q] + 8 * SXW);
+    iy0[q] = lds4(up[q] + 4 * SXW);
+  }
+  float nds[R][4]; uint32_t nvs[R][4];
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float iX1 = (i < 3) ? comp(fy[q], i + 1) : r[q];
+      const float iX0 = (i > 0) ? comp(fx[q], i - 1) : l[q];
+      float vx, vy;
+      nds[q][i] = band_apply_cell<EXT>(comp(d[q], i), comp(fx[q], i), comp(fy[q], i), comp(fz[q], i), comp(fw[q], i), iX1, iX0,
+                                       comp(iy1[q], i), comp(iy0[q], i), c, vx, vy);
+      nvs[q][i] = LAST ? pack_half2(vx, vy) : 0u;
+      if (EDGE && !(rc[q].row_in && (unsigned)(gx + i) < (unsigned)g.W)) { nds[q][i] = 0.f; nvs[q][i] = 0u; }
+    }
+    if (!LAST) {
+      d[q] = make_float4(nds[q][0], nds[q][1], nds[q][2], nds[q][3]);
+      sts4(me[q], add4(d[q], h[q]));
+    }
+  }
+  sy.arrive();
+  if (LAST) {
+#pragma unroll
+    for (int q = 0; q < R; ++q)
+      if (rc[q].store && st_col && !TWS_DBG_NOSTORE) {
+        st4(out.d + rc[q].go, make_float4(nds[q][0], nds[q][1], nds[q][2], nds[q][3]));
+        *reinterpret_cast<uint4*>(out.v + rc[q].go) = make_uint4(nvs[q][0], nvs[q][1], nvs[q][2], nvs[q][3]);
+      }
   }
 }
 
@@ -220,6 +372,7 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
   constexpr int K = C::K, NW = C::NW, R = C::R, BR = C::BR, SXW = C::SXW, HX = C::HX, OX = C::OX, HP = C::HP, LAND = C::LAND, XROW = C::XROW;
   extern __shared__ __align__(1024) float smem[];
   __shared__ uint64_t full_all[NW * C::NGRP];
+  __shared__ uint64_t gbar_all[C::NGRP];
   // read through volatile asm: the thread index stays in a register instead of being re-read (S2R, ~20
   // cycles of latency) and re-derived in every half-pass
   uint32_t tid_u;
@@ -227,7 +380,9 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
   const int tid = (int)tid_u, lane = tid & 31, grp = (tid >> 5) / NW, warp = (tid >> 5) - grp * NW;   // warp: index inside the group
   float* gsm = smem + grp * C::GROUP_FLOATS;              // this group's landing buffers | exchange slots | parking
   uint64_t* full = full_all + grp * NW + warp;
-  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(NW * 32) : "memory"); };
+  GroupSync sy;
+  sy.bar = smem_u32(&gbar_all[grp]);
+  sy.phase = 0;
   float* land = gsm + warp * (R * LAND);                  // R landing buffers of this warp
   const float* land_l = land + lane * 4;
   const uint32_t xch = smem_u32(gsm + BR * LAND + lane * 4);
@@ -257,9 +412,12 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
   if (tid == 0) {
 #pragma unroll 1
     for (int i = 0; i < NW * C::NGRP; ++i) mbar_init(&full_all[i], 1);
+#pragma unroll 1
+    for (int i = 0; i < C::NGRP; ++i) mbar_init(&gbar_all[i], NW);      // one arrival per warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();                                        // the only CTA-wide barrier: the mbarriers exist
+  sy.arrive();                                            // phase 0: "nobody is reading any exchange slot" (matched by the first wait)
   uint32_t parity = 0;
 
   const long long Rows = (long long)(lr1 - lr0);
@@ -280,8 +438,6 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
     const bool xedge = sx0 < 0 || sx0 + SXW > g.W;
     const int gx = sx0 + lane * 4;
     const bool st_col = lane * 4 >= HX && lane * 4 < HX + OX && gx < g.pitch;
-
-    group_sync();                                         // every warp of the group is done with the previous piece
 
     auto issue = [&](int i0) {                            // one lane: land the warp's R rows of the band starting at piece row i0
       if (!TWS_DBG_NOFENCE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -337,7 +493,8 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
       for (int q = 0; q < R; ++q) set_row(q, j, i0 + q * NW + warp);
       classify();
       // ---- half-pass 0: registers <- landing buffers; publish H; prefetch this warp's rows of the next band ----
-      if (i0 + warp < N) {
+      const bool loaded = i0 + warp < N;
+      if (loaded) {
         mbar_wait(full, parity);
         parity ^= 1u;
 #pragma unroll
@@ -349,51 +506,32 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
         }
         __syncwarp();
         if (lane == 0 && i0 + BR + warp < N) issue(i0 + BR);
+      }
+      sy.wait();                                          // the last half-pass of the previous band has read the slots these rows reuse
+      if (loaded) {
 #pragma unroll
         for (int q = 0; q < R; ++q) sts4(x_me[q], add4(d[q], h[q]));
       }
-      group_sync();
+      sy.arrive();
 
-      if (!carrier && plain) {
-        // ---- the common case: interior rows that start and finish inside this band ----
+      // ---- the 2K computing half-passes.  Carriers switch their last row once, before half-pass pw + 1;
+      // rows on the grid edge take the masked variants ----
+      const int swap_at = carrier ? pw + 1 : 0;
 #pragma unroll 1
-        for (int lv = 1; lv < K; ++lv) {
-          band_flux<R, SXW, false, false>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-          group_sync();
-          band_depth<R, SXW, false, false, EXT>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-          group_sync();
-        }
-        band_flux<R, SXW, false, true>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-        group_sync();
-        band_depth<R, SXW, false, true, EXT>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-        group_sync();
-      } else {
-        // ---- carriers (their last row changes mid-band) and rows on the grid edge ----
-        const int swap_at = carrier ? pw + 1 : 0;
-#pragma unroll 1
-        for (int s = 1; s <= HP; ++s) {
-          if (s == swap_at) swap_rows(j);
-          const bool last = s >= HP - 1;
-          if (s & 1) {
-            if (!plain) {
-              if (last) band_flux<R, SXW, true, true>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-              else band_flux<R, SXW, true, false>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-            } else {
-              if (last) band_flux<R, SXW, false, true>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-              else band_flux<R, SXW, false, false>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-            }
-          } else {
-            if (!plain) {
-              if (last) band_depth<R, SXW, true, true, EXT>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-              else band_depth<R, SXW, true, false, EXT>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-            } else {
-              if (last) band_depth<R, SXW, false, true, EXT>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-              else band_depth<R, SXW, false, false, EXT>(x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-            }
-          }
-          group_sync();
-        }
+      for (int lv = 1; lv < K; ++lv) {
+        if (2 * lv - 1 == swap_at) swap_rows(j);
+        if (plain) band_flux<R, SXW, false, false>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+        else band_flux<R, SXW, true, false>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+        if (2 * lv == swap_at) swap_rows(j);
+        if (plain) band_depth<R, SXW, false, false, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+        else band_depth<R, SXW, true, false, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
       }
+      if (HP - 1 == swap_at) swap_rows(j);
+      if (plain) band_flux<R, SXW, false, true>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+      else band_flux<R, SXW, true, true>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+      if (HP == swap_at) swap_rows(j);
+      if (plain) band_depth<R, SXW, false, true, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+      else band_depth<R, SXW, true, true, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
     }
   }
 }
