@@ -39,8 +39,9 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=8192, help="grid width (and per-GPU rows unless --strong)")
     ap.add_argument("--strong", action="store_true", help="fixed size x size grid split over the ranks (strong scaling)")
-    ap.add_argument("--backend", default="tb", choices=["unfused", "fused", "tb", "stream", "band"])
-    ap.add_argument("--tb", type=int, default=2, help="temporal block (steps per launch) for --backend tb / stream")
+    ap.add_argument("--backend", default="band", choices=["unfused", "fused", "tb", "stream", "band"],
+                    help="step kernel: band (default, lock-step row streaming), stream (ring row streaming), tb (overlapped tiles), fused (k=1 tiles), unfused")
+    ap.add_argument("--tb", type=int, default=4, help="temporal block (steps per launch, 1..4) for --backend band / stream / tb")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the end-to-end leg (default min(steps, 40))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -201,6 +202,7 @@ def workload_config(args, world):
                     f"open (reference) boundary, no sources; BASELINE config {'4/5 (strong)' if args.strong else '3 per GPU'}",
         "grid": [W, Hg], "backend": args.backend, "temporal_block": args.tb if args.backend in ("tb", "stream", "band") else 1,
         "decomposition": f"{world} row strip(s), halo rows pushed over NVLink by the step kernels' stream (no collective)",
+        "kernel_blocking": "column strips of 128 cells marched top to bottom, rows skewed in time (no halo rows recomputed), k steps per HBM round trip" if args.backend in ("band", "stream") else "overlapped tiles",
         "l2": "state >= 3.2 GB per GPU, far larger than the 126 MB L2 (inputs larger than L2, no flush needed)",
     }
 

@@ -71,6 +71,9 @@ struct BandRow {       // per-row context (the lane's column offset and store ma
 // runs while the other warps catch up.  Every warp alternates arrive / wait strictly, so a single
 // barrier and one phase bit per thread suffice (nobody can arrive for phase n+1 before it has seen
 // phase n complete).  TWS_BAND_SPLIT 0 degrades it to a plain barrier (arrive + wait back to back).
+#ifndef TWS_BAND_PACKED_SCALE
+#define TWS_BAND_PACKED_SCALE 1
+#endif
 #ifndef TWS_BAND_SPLIT
 #define TWS_BAND_SPLIT 1
 #endif
@@ -212,13 +215,21 @@ __device__ __forceinline__ void band_flux(GroupSync& sy, const uint32_t (&up)[R]
       }
   }
   // ---- scale and publish +-Y first: that is all the neighbour rows wait for ----
+  // (interior rows: packed multiplies; the products are only ever added to in a later half-pass, behind
+  // a barrier — tests/test_abi.py checks that ptxas did not contract any of them into an FFMA2)
 #pragma unroll
   for (int q = 0; q < R; ++q) {
-    float* pfz = &fz[q].x; float* pfw = &fw[q].x;
+    if (!EDGE && TWS_PACKED && TWS_BAND_PACKED_SCALE) {
+      const f2 slo = pk(scale[q][0], scale[q][1]), shi = pk(scale[q][2], scale[q][3]);
+      fz[q] = cat4(mul2(lo2(fz[q]), slo), mul2(hi2(fz[q]), shi));
+      fw[q] = cat4(mul2(lo2(fw[q]), slo), mul2(hi2(fw[q]), shi));
+    } else {
+      float* pfz = &fz[q].x; float* pfw = &fw[q].x;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      pfz[i] = __fmul_rn(pfz[i], scale[q][i]); pfw[i] = __fmul_rn(pfw[i], scale[q][i]);
-      if (EDGE && !(rc[q].row_in && (unsigned)(gx + i) < (unsigned)g.W)) { pfz[i] = 0.f; pfw[i] = 0.f; }
+      for (int i = 0; i < 4; ++i) {
+        pfz[i] = __fmul_rn(pfz[i], scale[q][i]); pfw[i] = __fmul_rn(pfw[i], scale[q][i]);
+        if (EDGE && !(rc[q].row_in && (unsigned)(gx + i) < (unsigned)g.W)) { pfz[i] = 0.f; pfw[i] = 0.f; }
+      }
     }
     sts4(me[q] + 4 * SXW, fz[q]);                // plane 1: +Y outflow, read by the row below
     sts4(me[q] + 8 * SXW, fw[q]);                // plane 2: -Y outflow, read by the row above
@@ -226,11 +237,17 @@ __device__ __forceinline__ void band_flux(GroupSync& sy, const uint32_t (&up)[R]
   sy.arrive();
 #pragma unroll
   for (int q = 0; q < R; ++q) {
-    float* pfx = &fx[q].x; float* pfy = &fy[q].x;
+    if (!EDGE && TWS_PACKED && TWS_BAND_PACKED_SCALE) {
+      const f2 slo = pk(scale[q][0], scale[q][1]), shi = pk(scale[q][2], scale[q][3]);
+      fx[q] = cat4(mul2(lo2(fx[q]), slo), mul2(hi2(fx[q]), shi));
+      fy[q] = cat4(mul2(lo2(fy[q]), slo), mul2(hi2(fy[q]), shi));
+    } else {
+      float* pfx = &fx[q].x; float* pfy = &fy[q].x;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      pfx[i] = __fmul_rn(pfx[i], scale[q][i]); pfy[i] = __fmul_rn(pfy[i], scale[q][i]);
-      if (EDGE && !(rc[q].row_in && (unsigned)(gx + i) < (unsigned)g.W)) { pfx[i] = 0.f; pfy[i] = 0.f; }
+      for (int i = 0; i < 4; ++i) {
+        pfx[i] = __fmul_rn(pfx[i], scale[q][i]); pfy[i] = __fmul_rn(pfy[i], scale[q][i]);
+        if (EDGE && !(rc[q].row_in && (unsigned)(gx + i) < (unsigned)g.W)) { pfx[i] = 0.f; pfy[i] = 0.f; }
+      }
     }
     if (LAST && rc[q].store && st_col && !TWS_DBG_NOSTORE) {
       st4(out.F[0] + rc[q].go, fx[q]); st4(out.F[1] + rc[q].go, fy[q]); st4(out.F[2] + rc[q].go, fz[q]); st4(out.F[3] + rc[q].go, fw[q]);
