@@ -216,15 +216,32 @@ tws_status tws_halo_connect(tws_sim* s, const tws_halo_handle* up, const tws_hal
 tws_status tws_halo_refresh(tws_sim* s);
 
 /* ---- renderer hand-off (CUDA-GL interop) --------------------------------------------
- * Registers the renderer's two textures: TerrainInfo RGBA32F (m_terrainData) and
- * FlowMap RG16F (m_waterFlowMap); tws_gl_publish writes (r=terrain,g=b=0.3,a=water)
- * and the flow vector into them.  Built only with -DTWS_WITH_GL (needs GL headers);
- * otherwise TWS_ERR_UNSUPPORTED.  tws_publish_packed is the same pack step into plain
- * device buffers the library owns (testable without GL). */
+ * Replaces the renderer's view of the simulation textures: m_terrainData (TerrainInfo, RGBA32F
+ * with the full mip chain the reference regenerates after every stepped frame,
+ * Terrain.cpp:272-276 + glEasy Texture2D.cpp:64-68) and m_waterFlowMap (FlowMap, RG16F, one
+ * level), sampled at Terrain.cpp:288,323-330.
+ *
+ * tws_gl_register takes the GL names of the renderer's two textures (flow_map_tex may be 0) and
+ * registers them with cudaGraphicsGLRegisterImage; the renderer's GL context must be current
+ * on the calling thread (otherwise TWS_ERR_CUDA).  tws_gl_publish writes (r = terrain,
+ * g = b = 0.3, a = water) plus the mip chain and the flow vectors into them.  Whole grids
+ * only (a strip returns TWS_ERR_UNSUPPORTED).
+ *
+ * The same data without GL: tws_publish_packed packs level 0 and the flow map into device
+ * buffers the library owns; tws_publish_mips additionally builds the mip chain, level L
+ * following level L-1 contiguously in one buffer (sizes / offsets: tws_mip_level_info);
+ * tws_readback_mip copies one published level to the host.  Mip rule (GL leaves the filter
+ * to the driver; pinned): tws_mip_levels = floor(log2(max(w,h))) + 1 levels (glEasy
+ * Texture.cpp:28-41), level L is max(1, w >> L) x max(1, h >> L), each texel the 2x2 box
+ * average ((t00 + t10) + (t01 + t11)) * 0.25 of level L-1, source coordinates clamped. */
 tws_status tws_gl_register(tws_sim* s, uint32_t terrain_info_tex, uint32_t flow_map_tex);
 tws_status tws_gl_publish(tws_sim* s);
 tws_status tws_gl_unregister(tws_sim* s);
 tws_status tws_publish_packed(tws_sim* s, void** terrain_info_rgba32f_dev, void** flow_map_rg16f_dev);
+tws_status tws_publish_mips(tws_sim* s, void** terrain_info_chain_rgba32f_dev, int32_t* levels);
+tws_status tws_readback_mip(tws_sim* s, int32_t level, void* host, size_t bytes);
+int32_t    tws_mip_levels(int32_t width, int32_t height);
+tws_status tws_mip_level_info(int32_t width, int32_t height, int32_t level, int32_t* w, int32_t* h, int64_t* offset_texels);
 
 #ifdef __cplusplus
 }

@@ -138,3 +138,32 @@ def dam_break(W: int = 256, H: Optional[int] = None, rim: bool = True):
             a[0, :] = 1000.0; a[-1, :] = 1000.0; a[:, 0] = 1000.0; a[:, -1] = 1000.0
         d[0, :] = 0; d[-1, :] = 0; d[:, 0] = 0; d[:, -1] = 0
     return h, d
+
+
+def mip_levels(W: int, H: int) -> int:
+    """Level count of the reference's texture wrapper (glEasy Texture.cpp:28-41): halve every side until all are 0."""
+    n = 0
+    while W > 0 or H > 0:
+        W //= 2; H //= 2; n += 1
+    return n
+
+
+def mip_chain(level0: np.ndarray) -> list:
+    """Restatement of `m_terrainData->GenMipMaps()` (Terrain.cpp:272-276 -> glEasy Texture2D.cpp:64-68,
+    glGenerateMipmap) for an (H, W, C) float32 image.  GL leaves the filter to the driver, so it is PINNED
+    (DESIGN.md section 5), not taken from the reference: level L has max(1, side >> L) texels per side
+    (the glTexStorage2D rule), each the 2x2 box average ((t00 + t10) + (t01 + t11)) * 0.25 of level L-1 in
+    binary32, source coordinates clamped to the source."""
+    assert level0.dtype == np.float32 and level0.ndim == 3
+    out = [level0]
+    H, W = level0.shape[:2]
+    for _ in range(1, mip_levels(W, H)):
+        src = out[-1]
+        sh, sw = src.shape[:2]
+        dh, dw = max(1, sh >> 1), max(1, sw >> 1)
+        y0 = np.minimum(2 * np.arange(dh), sh - 1); y1 = np.minimum(2 * np.arange(dh) + 1, sh - 1)
+        x0 = np.minimum(2 * np.arange(dw), sw - 1); x1 = np.minimum(2 * np.arange(dw) + 1, sw - 1)
+        top = src[y0][:, x0] + src[y0][:, x1]          # float32 adds, rounded once each
+        bot = src[y1][:, x0] + src[y1][:, x1]
+        out.append(((top + bot) * np.float32(0.25)).astype(np.float32))
+    return out

@@ -109,6 +109,10 @@ SYMBOLS = {
     "tws_gl_publish": (C.c_int, [_SIM]),
     "tws_gl_unregister": (C.c_int, [_SIM]),
     "tws_publish_packed": (C.c_int, [_SIM, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "tws_publish_mips": (C.c_int, [_SIM, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
+    "tws_readback_mip": (C.c_int, [_SIM, C.c_int32, C.c_void_p, C.c_size_t]),
+    "tws_mip_levels": (C.c_int32, [C.c_int32, C.c_int32]),
+    "tws_mip_level_info": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
 }
 
 _lib = None

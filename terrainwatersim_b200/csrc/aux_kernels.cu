@@ -143,6 +143,34 @@ cudaError_t launch_pack_info(const Geom& g, const Planes& p, int side, float* ao
   return cudaGetLastError();
 }
 
+// ---- mip chain of TerrainInfo ---------------------------------------------------------------------
+// The reference regenerates the full mip chain of m_terrainData after every frame that stepped
+// (Terrain.cpp:272-276 -> Texture2D::GenMipMaps, glEasy Texture2D.cpp:64-68: glGenerateMipmap).  GL
+// leaves the filter to the driver; pinned here: level L has max(1, size >> L)
+// texels per side, each the 2x2 box average ((t00 + t10) + (t01 + t11)) * 0.25 of level L-1 per
+// channel, source coordinates clamped to the source (a side that has shrunk to 1 keeps averaging
+// the other).  One thread per destination texel; levels >= 1 hold a third of level 0 in total.
+__global__ void __launch_bounds__(256) mip_level_kernel(const float4* __restrict__ src, int sw, int sh, float4* __restrict__ dst, int dw, int dh) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= dw) return;
+  for (int y = blockIdx.y; y < dh; y += gridDim.y) {
+    const int x0 = min(2 * x, sw - 1), x1 = min(2 * x + 1, sw - 1);
+    const long long r0 = (long long)min(2 * y, sh - 1) * sw, r1 = (long long)min(2 * y + 1, sh - 1) * sw;
+    const float4 a = src[r0 + x0], b = src[r0 + x1], c = src[r1 + x0], d = src[r1 + x1];
+    float4 o;
+    o.x = __fmul_rn(__fadd_rn(__fadd_rn(a.x, b.x), __fadd_rn(c.x, d.x)), 0.25f);
+    o.y = __fmul_rn(__fadd_rn(__fadd_rn(a.y, b.y), __fadd_rn(c.y, d.y)), 0.25f);
+    o.z = __fmul_rn(__fadd_rn(__fadd_rn(a.z, b.z), __fadd_rn(c.z, d.z)), 0.25f);
+    o.w = __fmul_rn(__fadd_rn(__fadd_rn(a.w, b.w), __fadd_rn(c.w, d.w)), 0.25f);
+    dst[(long long)y * dw + x] = o;
+  }
+}
+cudaError_t launch_mip_level(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t st) {
+  dim3 block(256), grid((dw + 255) / 256, dh < 2048 ? dh : 2048);
+  mip_level_kernel<<<grid, block, 0, st>>>((const float4*)src, sw, sh, (float4*)dst, dw, dh);
+  return cudaGetLastError();
+}
+
 // ---- fp64 volume: fixed-shape two-stage reduction (deterministic) ------------------------------
 __global__ void __launch_bounds__(256) volume_kernel(Geom g, const float* __restrict__ d /* local row 0 */, double* partials) {
   double acc = 0.0;

@@ -36,6 +36,8 @@
 // them keeps the half-pass free of per-row branches.
 #include "cell_math.cuh"
 
+#include <algorithm>
+
 namespace tws {
 
 template <int K_, int NW_, int R_, int NGRP_>
@@ -62,6 +64,22 @@ struct BandRow {       // per-row context (the lane's column offset and store ma
   bool row_in;         // the row exists in the global grid
   bool store;          // the row is an output row of this piece
   size_t go;           // element offset of the lane's group in the output planes
+};
+
+// Work list of one launch.  A piece is (row segment, column strip); every warp group starts on piece
+// `its index` and then takes pieces from a device-wide counter, so groups whose cells need the slow
+// paths (the IEEE division of draining wet cells: lake and shore regions cost up to 1.4x the
+// instructions of dry land) simply take fewer pieces.  Segments shrink geometrically down the strip
+// ("guided" schedule: about half of the remaining rows per level), so the pieces handed out last are
+// small and the groups finish together, while most rows are covered by long pieces whose 2K warm-up /
+// feeder rows amortise.  Piece p = (segment p / nstrips, strip p % nstrips): the pieces in flight at any
+// time are the same rows of neighbouring strips, which keeps their shared halo columns in L2.
+struct BandSched {
+  static constexpr int MAXLEV = 12;
+  int nlev, npieces, rows;
+  int seg0[MAXLEV];    // first segment of level l
+  int y0[MAXLEV];      // first row (relative to lr0) of level l
+  int size[MAXLEV];    // rows per segment of level l (the last segment of a level may be shorter)
 };
 
 // Split-phase group barrier: one mbarrier per warp group, one arrival per warp.  arrive() right after a
@@ -384,12 +402,14 @@ __device__ __forceinline__ void band_depth(GroupSync& sy, const uint32_t (&up)[R
 template <class C, bool EXT>
 __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_constant__ CUtensorMap tm_h,
                                                              const __grid_constant__ CUtensorMap tm_s,
+                                                             const __grid_constant__ BandSched sch,
                                                              FusedOut out, Geom g, StepConsts c, int lr0, int lr1, int nstrips,
-                                                             int tma_y_bias) {
+                                                             int tma_y_bias, uint32_t* sched) {
   constexpr int K = C::K, NW = C::NW, R = C::R, BR = C::BR, SXW = C::SXW, HX = C::HX, OX = C::OX, HP = C::HP, LAND = C::LAND, XROW = C::XROW;
   extern __shared__ __align__(1024) float smem[];
   __shared__ uint64_t full_all[NW * C::NGRP];
   __shared__ uint64_t gbar_all[C::NGRP];
+  __shared__ int next_piece[C::NGRP][2];
   // read through volatile asm: the thread index stays in a register instead of being re-read (S2R, ~20
   // cycles of latency) and re-derived in every half-pass
   uint32_t tid_u;
@@ -437,17 +457,24 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
   sy.arrive();                                            // phase 0: "nobody is reading any exchange slot" (matched by the first wait)
   uint32_t parity = 0;
 
-  const long long Rows = (long long)(lr1 - lr0);
-  const long long TR = Rows * nstrips;
-  const long long vcta = (long long)blockIdx.x * C::NGRP + grp, nvcta = (long long)gridDim.x * C::NGRP;   // every group is a virtual CTA
-  const long long lin_begin = TR * vcta / nvcta, lin_end = TR * (vcta + 1) / nvcta;
+  // every group is a virtual CTA; its first piece is static, the following ones come from the counter
+  const int vcta = (int)blockIdx.x * C::NGRP + grp, nvcta = (int)gridDim.x * C::NGRP;
+  int piece = vcta, pp = 0;
 
 #pragma unroll 1
-  for (long long lin = lin_begin; lin < lin_end;) {
-    const int strip = (int)(lin / Rows);
-    const int ya = lr0 + (int)(lin - (long long)strip * Rows);
-    const int yb = (int)((long long)ya + (lin_end - lin) < (long long)lr1 ? (long long)ya + (lin_end - lin) : (long long)lr1);
-    lin += yb - ya;
+  while (piece < sch.npieces) {
+    // fetch the piece after this one now: the atomic's round trip hides behind the whole piece; the group reads
+    // the slot after the piece's barriers (release / acquire), and the two slots alternate so that the next
+    // write cannot overtake a reader
+    if (sched && warp == 0 && lane == 0) next_piece[grp][pp] = nvcta + (int)atomicAdd(sched, 1u);
+    const int seg = piece / nstrips, strip = piece - seg * nstrips;
+    int lev = 0;
+#pragma unroll 1
+    while (lev + 1 < sch.nlev && seg >= sch.seg0[lev + 1]) ++lev;
+    const int lev_end = lev + 1 < sch.nlev ? sch.y0[lev + 1] : sch.rows;
+    const int ya_rel = sch.y0[lev] + (seg - sch.seg0[lev]) * sch.size[lev];
+    const int ya = lr0 + ya_rel;
+    const int yb = lr0 + (ya_rel + sch.size[lev] < lev_end ? ya_rel + sch.size[lev] : lev_end);
     const int sx0 = strip * OX - HX;
     const int ystart = ya - HP;                           // 2K warm-up rows above, 2K feeder rows below
     const int N = (yb - ya) + 2 * HP;
@@ -550,6 +577,15 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
       if (plain) band_depth<R, SXW, false, true, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
       else band_depth<R, SXW, true, true, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
     }
+    piece = sched ? *(volatile int*)&next_piece[grp][pp] : piece + nvcta;
+    pp ^= 1;
+  }
+  // the last group to leave re-arms the counters for the next launch on this stream (every group that had a
+  // piece has by then seen its final, failing fetch, so no atomic on the counter is still in flight)
+  if (sched && vcta < sch.npieces && warp == 0 && lane == 0) {
+    const unsigned active = (unsigned)(nvcta < sch.npieces ? nvcta : sch.npieces);
+    __threadfence();
+    if (atomicAdd(sched + 1, 1u) == active - 1u) { sched[0] = 0u; sched[1] = 0u; }
   }
 }
 
@@ -577,9 +613,35 @@ static int band_sm_count() {
   return cached[dev & 63] > 0 ? cached[dev & 63] : 148;
 }
 
+// Guided schedule for `rows` rows of `nstrips` strips on up to `max_groups` warp groups (see BandSched).
+static BandSched band_schedule(int rows, int nstrips, int max_groups, int BR) {
+  BandSched s{};
+  const long long total = (long long)rows * nstrips;
+  const int even = (int)((total + max_groups - 1) / max_groups);            // rows per group if the work were split evenly
+  // shortest segment: long enough that the 2K warm-up / feeder rows and the extra band amortise (128 rows), but
+  // small grids are latency bound and rather use every SM (at least ~4 bands per piece)
+  const int smin = std::max(4 * BR, std::min(128, even));
+  int size = std::max(smin, even / 2);
+  int y = 0, seg = 0, l = 0;
+  while (y < rows) {
+    const int rem = rows - y;
+    const bool rest = size <= smin || l == BandSched::MAXLEV - 1;
+    const int n = rest ? (rem + size - 1) / size : std::max(1, rem / 2 / size);   // about half of what is left per level
+    s.seg0[l] = seg; s.y0[l] = y; s.size[l] = size;
+    seg += n;
+    y += (int)std::min<long long>(rem, (long long)n * size);
+    ++l;
+    size = std::max(smin, size / 2);
+  }
+  s.nlev = l;
+  s.rows = rows;
+  s.npieces = seg * nstrips;
+  return s;
+}
+
 template <int K, bool EXT>
 static cudaError_t launch_band_k(const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, uint32_t* sched) {
   using C = typename BandCfgFor<K>::type;
   if (C::SXW != stream_strip_width()) return cudaErrorInvalidValue;      // ring and band kernels share the row descriptors
   static bool attr_set[64] = {};
@@ -599,25 +661,24 @@ static cudaError_t launch_band_k(const Geom& g, const Planes& p, const TmaSet& t
   for (int i = 0; i < 4; ++i) out.F[i] = p.F[dst][i] + row0_off;
   out.v = p.v + row0_off;
   const int nstrips = (g.W + C::OX - 1) / C::OX;
-  const long long total_rows = (long long)nstrips * (lr1 - lr0);
-  // one persistent CTA per SM; small grids: at least ~4 bands of rows per group so the 4K warm-up / feeder rows amortise
-  const long long min_rows = 4LL * C::BR * C::NGRP;
-  long long want = (total_rows + min_rows - 1) / min_rows;
+  // one persistent CTA per SM (fewer when there are fewer pieces than warp groups)
   const int sms = band_sm_count();
-  const int grid = (int)(want < 1 ? 1 : (want < sms ? want : sms));
+  const BandSched sch = band_schedule(lr1 - lr0, nstrips, sms * C::NGRP, C::BR);
+  const int want = (sch.npieces + C::NGRP - 1) / C::NGRP;
+  const int grid = want < 1 ? 1 : (want < sms ? want : sms);
   const int bias = g.has_up ? TWS_HALO_ROWS : 0;
-  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], out, g, c, lr0, lr1, nstrips, bias);
+  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], sch, out, g, c, lr0, lr1, nstrips, bias, sched);
   return cudaGetLastError();
 }
 
 cudaError_t launch_band(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
-                        cudaStream_t st) {
+                        cudaStream_t st, uint32_t* sched) {
   const bool ext = c.ext_sources != 0;
   switch (K) {
-    case 1: return ext ? launch_band_k<1, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<1, false>(g, p, tma, src, c, lr0, lr1, st);
-    case 2: return ext ? launch_band_k<2, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<2, false>(g, p, tma, src, c, lr0, lr1, st);
-    case 3: return ext ? launch_band_k<3, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<3, false>(g, p, tma, src, c, lr0, lr1, st);
-    case 4: return ext ? launch_band_k<4, true>(g, p, tma, src, c, lr0, lr1, st) : launch_band_k<4, false>(g, p, tma, src, c, lr0, lr1, st);
+    case 1: return ext ? launch_band_k<1, true>(g, p, tma, src, c, lr0, lr1, st, sched) : launch_band_k<1, false>(g, p, tma, src, c, lr0, lr1, st, sched);
+    case 2: return ext ? launch_band_k<2, true>(g, p, tma, src, c, lr0, lr1, st, sched) : launch_band_k<2, false>(g, p, tma, src, c, lr0, lr1, st, sched);
+    case 3: return ext ? launch_band_k<3, true>(g, p, tma, src, c, lr0, lr1, st, sched) : launch_band_k<3, false>(g, p, tma, src, c, lr0, lr1, st, sched);
+    case 4: return ext ? launch_band_k<4, true>(g, p, tma, src, c, lr0, lr1, st, sched) : launch_band_k<4, false>(g, p, tma, src, c, lr0, lr1, st, sched);
     default: return cudaErrorInvalidValue;
   }
 }

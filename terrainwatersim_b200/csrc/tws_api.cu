@@ -64,6 +64,9 @@ struct tws_sim {
   size_t staging_bytes = 0;
   void* packed_info = nullptr;       // publish buffers
   void* packed_flow = nullptr;
+  int published_levels = 0;          // mip levels of TerrainInfo currently valid in packed_info
+  cudaGraphicsResource* gl_info = nullptr;   // renderer textures registered with tws_gl_register
+  cudaGraphicsResource* gl_flow = nullptr;
   // Captured step batches (frame scheduler): one executable graph per (n, ping-pong side).
   struct StepGraph { int n; int cur; int cur_after; uint64_t launches; cudaGraphExec_t exec; };
   std::vector<StepGraph> graphs;
@@ -223,7 +226,7 @@ tws_status run_block_stream(tws_sim* s, int k) {
   tws_status r = ensure_tma_stream(s);
   if (r) return r;
   if (!strip) {
-    TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, g.rows, s->st_main, stream_impl(s)));
+    TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, g.rows, s->st_main, stream_impl(s), s->ctrl->sched_main));
     s->launches += 1;
     s->cur = 1 - src;
     return TWS_OK;
@@ -233,13 +236,13 @@ tws_status run_block_stream(tws_sim* s, int k) {
   const int i0 = e_top, i1 = g.rows - e_bot;
   TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));
   if (i1 > i0) {
-    TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i0, i1, s->st_main, stream_impl(s)));
+    TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i0, i1, s->st_main, stream_impl(s), s->ctrl->sched_main));
     s->launches += 1;
   }
   TWS_CUDA(s, cudaStreamWaitEvent(s->st_edge, s->ev_main, 0));
   TWS_CUDA(s, launch_wait_flags(s->ctrl, g.has_up, g.has_down, s->epoch, s->st_edge)); s->launches++;
-  if (e_top > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, e_top, s->st_edge, stream_impl(s))); s->launches++; }
-  if (e_bot > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i1, g.rows, s->st_edge, stream_impl(s))); s->launches++; }
+  if (e_top > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, e_top, s->st_edge, stream_impl(s), s->ctrl->sched_edge)); s->launches++; }
+  if (e_bot > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i1, g.rows, s->st_edge, stream_impl(s), s->ctrl->sched_edge)); s->launches++; }
   r = push_edges(s, 1 - src, false, s->st_edge); if (r) return r;
   r = post_and_count(s, s->st_edge); if (r) return r;
   TWS_CUDA(s, cudaEventRecord(s->ev_edge, s->st_edge));
@@ -318,7 +321,7 @@ tws_status run_batch_graph(tws_sim* s, int n, int K, bool* done) {
   // make sure nothing but kernel launches happens inside the capture
   if (is_stream_backend(s->prm.backend)) {
     tws_status r = ensure_tma_stream(s); if (r) return r;
-    for (int k : {K, n % K}) if (k > 0) TWS_CUDA(s, launch_stream(k, s->geom, s->planes, s->tma_stream[0], 0, s->consts, 0, 0, s->st_main, stream_impl(s)));
+    for (int k : {K, n % K}) if (k > 0) TWS_CUDA(s, launch_stream(k, s->geom, s->planes, s->tma_stream[0], 0, s->consts, 0, 0, s->st_main, stream_impl(s), s->ctrl->sched_main));
   } else if (s->prm.backend != TWS_BACKEND_UNFUSED) {
     for (int k : {K, n % K}) if (k > 0) {
       tws_status r = ensure_tma(s, k); if (r) return r;
@@ -492,6 +495,7 @@ tws_status tws_destroy(tws_sim* s) {
   if (s->staging) cudaFree(s->staging);
   if (s->partials) cudaFree(s->partials);
   if (s->white_dev) cudaFree(s->white_dev);
+  tws_gl_unregister(s);
   if (s->packed_info) cudaFree(s->packed_info);
   if (s->packed_flow) cudaFree(s->packed_flow);
   if (s->slab) cudaFree(s->slab);
@@ -722,7 +726,7 @@ tws_status tws_step_host(tws_sim* s, const float* water_in, float* water_out, vo
     int r0, r1; band_rows(b, &r0, &r1);
     if (water_in) TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->band_ev[2 * std::min(b + 1, nb - 1)], 0));
     const int u0 = b * band_units, u1 = std::min(units, (b + 1) * band_units);
-    if (stream_be) TWS_CUDA(s, launch_stream(1, g, s->planes, s->tma_stream[src], src, s->consts, r0, r1, s->st_main, stream_impl(s)));
+    if (stream_be) TWS_CUDA(s, launch_stream(1, g, s->planes, s->tma_stream[src], src, s->consts, r0, r1, s->st_main, stream_impl(s), s->ctrl->sched_main));
     else TWS_CUDA(s, launch_fused(1, g, s->planes, s->tma[1][src], src, s->consts, u0, u1, s->st_main));
     s->launches += 1;
     TWS_CUDA(s, cudaEventRecord(s->band_ev[2 * b + 1], s->st_main));
@@ -897,26 +901,162 @@ tws_status tws_halo_refresh(tws_sim* s) {
 }
 
 // ---- renderer hand-off -------------------------------------------------------------------------
-tws_status tws_publish_packed(tws_sim* s, void** info, void** flow) {
-  if (!s || !info || !flow) return TWS_ERR_INVALID;
-  DeviceGuard guard(s->prm.device);
+// Level count and sizes follow the reference's texture wrapper: glEasy Texture.cpp:28-41 counts
+// halvings until every side is 0 (floor(log2(max side)) + 1 levels), glTexStorage2D gives level L
+// max(1, side >> L) texels per side.
+int32_t tws_mip_levels(int32_t width, int32_t height) {
+  int32_t n = 0;
+  while (width > 0 || height > 0) { width /= 2; height /= 2; ++n; }
+  return n;
+}
+
+tws_status tws_mip_level_info(int32_t width, int32_t height, int32_t level, int32_t* w, int32_t* h, int64_t* offset_texels) {
+  if (width < 1 || height < 1 || level < 0 || level >= tws_mip_levels(width, height)) return TWS_ERR_INVALID;
+  int64_t off = 0;
+  for (int32_t l = 0; l < level; ++l) off += (int64_t)std::max(1, width >> l) * std::max(1, height >> l);
+  if (w) *w = std::max(1, width >> level);
+  if (h) *h = std::max(1, height >> level);
+  if (offset_texels) *offset_texels = off;
+  return TWS_OK;
+}
+
+namespace {
+size_t mip_chain_texels(int w, int h) {
+  size_t n = 0;
+  for (int l = 0, L = tws_mip_levels(w, h); l < L; ++l) n += (size_t)std::max(1, w >> l) * std::max(1, h >> l);
+  return n;
+}
+// level 0 of TerrainInfo (and the flow map) into the publish buffers; the info buffer has room for the whole chain
+tws_status publish_level0(tws_sim* s) {
   const Geom& g = s->geom;
   const size_t cells = (size_t)g.W * g.rows;
-  if (!s->packed_info) TWS_CUDA(s, cudaMalloc(&s->packed_info, cells * 16));
+  if (!s->packed_info) TWS_CUDA(s, cudaMalloc(&s->packed_info, mip_chain_texels(g.W, g.rows) * 16));
   if (!s->packed_flow) TWS_CUDA(s, cudaMalloc(&s->packed_flow, cells * 4));
   if (g.has_up || g.has_down) TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));
   TWS_CUDA(s, launch_pack_info(g, s->planes, s->cur, (float*)s->packed_info, 0, g.rows, true, s->st_main));
   s->launches += 1;
   TWS_CUDA(s, cudaMemcpy2DAsync(s->packed_flow, (size_t)g.W * 4, s->planes.v + (size_t)TWS_HALO_ROWS * g.pitch, (size_t)g.pitch * 4,
                                 (size_t)g.W * 4, g.rows, cudaMemcpyDeviceToDevice, s->st_main));
+  s->published_levels = 1;
+  return TWS_OK;
+}
+// levels 1.. of the published TerrainInfo (Terrain.cpp:272-276); whole grids only: a strip cannot filter across its seam
+tws_status publish_chain(tws_sim* s) {
+  const Geom& g = s->geom;
+  if (g.has_up || g.has_down || g.rows != g.Hg)
+    return fail(s, TWS_ERR_UNSUPPORTED, "the mip chain is built for whole grids only (publish level 0 per strip and filter on the renderer's GPU)");
+  tws_status r = publish_level0(s);
+  if (r) return r;
+  const int L = tws_mip_levels(g.W, g.rows);
+  float* base = (float*)s->packed_info;
+  for (int l = 1; l < L; ++l) {
+    int32_t sw, sh, dw, dh; int64_t so, d_o;
+    tws_mip_level_info(g.W, g.rows, l - 1, &sw, &sh, &so);
+    tws_mip_level_info(g.W, g.rows, l, &dw, &dh, &d_o);
+    TWS_CUDA(s, launch_mip_level(base + so * 4, sw, sh, base + d_o * 4, dw, dh, s->st_main));
+    s->launches += 1;
+  }
+  s->published_levels = L;
+  return TWS_OK;
+}
+}  // namespace
+
+tws_status tws_publish_packed(tws_sim* s, void** info, void** flow) {
+  if (!s || !info || !flow) return TWS_ERR_INVALID;
+  DeviceGuard guard(s->prm.device);
+  tws_status r = publish_level0(s);
+  if (r) return r;
   *info = s->packed_info; *flow = s->packed_flow;
   return TWS_OK;
 }
 
-#ifndef TWS_WITH_GL
-tws_status tws_gl_register(tws_sim* s, uint32_t, uint32_t) { return fail(s, TWS_ERR_UNSUPPORTED, "libtws was built without TWS_WITH_GL (no GL headers in this image)"); }
-tws_status tws_gl_publish(tws_sim* s) { return fail(s, TWS_ERR_UNSUPPORTED, "libtws was built without TWS_WITH_GL"); }
-tws_status tws_gl_unregister(tws_sim* s) { return fail(s, TWS_ERR_UNSUPPORTED, "libtws was built without TWS_WITH_GL"); }
-#endif
+tws_status tws_publish_mips(tws_sim* s, void** info_chain, int32_t* levels) {
+  if (!s || !info_chain) return TWS_ERR_INVALID;
+  DeviceGuard guard(s->prm.device);
+  tws_status r = publish_chain(s);
+  if (r) return r;
+  *info_chain = s->packed_info;
+  if (levels) *levels = s->published_levels;
+  return TWS_OK;
+}
+
+tws_status tws_readback_mip(tws_sim* s, int32_t level, void* host, size_t bytes) {
+  if (!s || !host) return TWS_ERR_INVALID;
+  DeviceGuard guard(s->prm.device);
+  if (level < 0 || level >= s->published_levels) return fail(s, TWS_ERR_STATE, "tws_readback_mip: level not published (call tws_publish_mips first)");
+  int32_t w, h; int64_t off;
+  tws_mip_level_info(s->geom.W, s->geom.rows, level, &w, &h, &off);
+  if (bytes != (size_t)w * h * 16) return fail(s, TWS_ERR_INVALID, "tws_readback_mip: byte count does not match the level (w*h*16)");
+  TWS_CUDA(s, cudaMemcpyAsync(host, (const float*)s->packed_info + off * 4, bytes, cudaMemcpyDeviceToHost, s->st_main));
+  TWS_CUDA(s, cudaStreamSynchronize(s->st_main));
+  return TWS_OK;
+}
+
+// CUDA-GL interop.  <cuda_gl_interop.h> needs <GL/gl.h>, which a headless build image does not ship; the
+// one GL-specific entry point lives in libcudart itself and takes plain GL object names, so it is declared
+// here with the GL typedefs spelled out (GLuint = GLenum = unsigned int).  The calling thread must have the
+// renderer's GL context current (the reference is single-threaded: RenderWindow.cpp:103-108); without one
+// the CUDA runtime reports an error and the call fails with TWS_ERR_CUDA.
+extern "C" cudaError_t cudaGraphicsGLRegisterImage(struct cudaGraphicsResource** resource, unsigned int image, unsigned int target,
+                                                   unsigned int flags);
+static constexpr unsigned int kGlTexture2D = 0x0DE1;   // GL_TEXTURE_2D
+
+tws_status tws_gl_unregister(tws_sim* s) {
+  if (!s) return TWS_ERR_INVALID;
+  DeviceGuard guard(s->prm.device);
+  for (cudaGraphicsResource** r : {&s->gl_info, &s->gl_flow})
+    if (*r) { cudaGraphicsUnregisterResource(*r); *r = nullptr; }
+  return TWS_OK;
+}
+
+tws_status tws_gl_register(tws_sim* s, uint32_t terrain_info_tex, uint32_t flow_map_tex) {
+  if (!s) return TWS_ERR_INVALID;
+  DeviceGuard guard(s->prm.device);
+  if (s->geom.has_up || s->geom.has_down) return fail(s, TWS_ERR_UNSUPPORTED, "tws_gl_register: whole grids only (the renderer samples one texture)");
+  tws_gl_unregister(s);
+  cudaError_t e = cudaGraphicsGLRegisterImage(&s->gl_info, terrain_info_tex, kGlTexture2D, cudaGraphicsRegisterFlagsWriteDiscard);
+  if (e == cudaSuccess && flow_map_tex)
+    e = cudaGraphicsGLRegisterImage(&s->gl_flow, flow_map_tex, kGlTexture2D, cudaGraphicsRegisterFlagsWriteDiscard);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    tws_gl_unregister(s);
+    return cuda_fail(s, e, "tws_gl_register: cudaGraphicsGLRegisterImage (is the renderer's GL context current on this thread?)");
+  }
+  return TWS_OK;
+}
+
+// One frame's hand-off: TerrainInfo level 0 (r = terrain, g = b = 0.3, a = water) plus the mip chain the
+// reference regenerates (Terrain.cpp:272-276) into the RGBA32F texture, the flow vectors into the RG16F one.
+// Levels the texture does not have (it was allocated with fewer) end the copy loop quietly.
+tws_status tws_gl_publish(tws_sim* s) {
+  if (!s) return TWS_ERR_INVALID;
+  if (!s->gl_info) return fail(s, TWS_ERR_STATE, "tws_gl_publish before tws_gl_register");
+  DeviceGuard guard(s->prm.device);
+  tws_status r = publish_chain(s);
+  if (r) return r;
+  const Geom& g = s->geom;
+  cudaGraphicsResource* res[2] = {s->gl_info, s->gl_flow};
+  const int nres = s->gl_flow ? 2 : 1;
+  TWS_CUDA(s, cudaGraphicsMapResources(nres, res, s->st_main));
+  cudaError_t e = cudaSuccess;
+  for (int l = 0; l < s->published_levels && e == cudaSuccess; ++l) {
+    int32_t w, h; int64_t off;
+    tws_mip_level_info(g.W, g.rows, l, &w, &h, &off);
+    cudaArray_t arr = nullptr;
+    if (cudaGraphicsSubResourceGetMappedArray(&arr, s->gl_info, 0, (unsigned)l) != cudaSuccess) { cudaGetLastError(); break; }
+    e = cudaMemcpy2DToArrayAsync(arr, 0, 0, (const float*)s->packed_info + off * 4, (size_t)w * 16, (size_t)w * 16, (size_t)h,
+                                 cudaMemcpyDeviceToDevice, s->st_main);
+  }
+  if (e == cudaSuccess && s->gl_flow) {
+    cudaArray_t arr = nullptr;
+    e = cudaGraphicsSubResourceGetMappedArray(&arr, s->gl_flow, 0, 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DToArrayAsync(arr, 0, 0, s->packed_flow, (size_t)g.W * 4, (size_t)g.W * 4, (size_t)g.rows, cudaMemcpyDeviceToDevice, s->st_main);
+  }
+  cudaError_t eu = cudaGraphicsUnmapResources(nres, res, s->st_main);   // unmap orders the copies before the renderer's next GL use
+  if (e != cudaSuccess) return cuda_fail(s, e, "tws_gl_publish: copy into the mapped texture");
+  if (eu != cudaSuccess) return cuda_fail(s, eu, "tws_gl_publish: cudaGraphicsUnmapResources");
+  return TWS_OK;
+}
 
 }  // extern "C"

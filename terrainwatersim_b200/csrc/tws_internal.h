@@ -31,6 +31,10 @@ struct Control {
   alignas(128) volatile uint32_t flag_from_up;
   alignas(128) volatile uint32_t flag_from_down;
   alignas(128) uint32_t error;       // set by the wait kernel on timeout
+  // Piece counters of the band kernel's dynamic schedule, {next piece, groups done}: one pair per stream
+  // that launches step kernels (launches on one stream are ordered, the pair is re-armed by the kernel itself).
+  alignas(128) uint32_t sched_main[2];
+  alignas(128) uint32_t sched_edge[2];
 };
 
 struct StepConsts {
@@ -77,11 +81,12 @@ cudaError_t build_tma_boxes(const Geom& g, const Planes& p, int side, int box_x,
 cudaError_t build_tma_rows(const Geom& g, const Planes& p, int side, int box_x, TmaSet* out, std::string* err, int l2_promotion);
 cudaError_t stream_build_tma(const Geom& g, const Planes& p, int side, TmaSet* out, std::string* err);
 // impl 0: ring kernel (one warp per row, per-row barriers); impl 1: band kernel (CTA-synchronous skewed bands).
+// sched: the Control counter pair of the launching stream (band kernel; nullptr = static round-robin pieces).
 cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c,
-                          int lr0, int lr1, cudaStream_t st, int impl);
+                          int lr0, int lr1, cudaStream_t st, int impl, uint32_t* sched);
 // Band kernel (band_kernels.cu): the streaming schedule in lock step; same row descriptors as the ring kernel.
 cudaError_t launch_band(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c,
-                        int lr0, int lr1, cudaStream_t st);
+                        int lr0, int lr1, cudaStream_t st, uint32_t* sched);
 int stream_strip_width();
 cudaError_t launch_unfused_update(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st);
 cudaError_t launch_unfused_apply(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st);
@@ -92,6 +97,8 @@ cudaError_t launch_scene(const Geom& g, const Planes& p, int side, const float* 
                          float persistence, cudaStream_t st);
 cudaError_t launch_pack_flux(const Geom& g, const Planes& p, int side, float* aos, int lr0, int nrows, bool to_aos, cudaStream_t st);
 cudaError_t launch_pack_info(const Geom& g, const Planes& p, int side, float* aos, int lr0, int nrows, bool to_aos, cudaStream_t st);
+// one level of the RGBA32F mip chain (2x2 box, see aux_kernels.cu): dst (dw x dh texels) <- src (sw x sh texels)
+cudaError_t launch_mip_level(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t st);
 cudaError_t launch_boundary_outflow(const Geom& g, const Planes& p, int side, double* out, cudaStream_t st);
 cudaError_t launch_volume(const Geom& g, const float* d, double* partials, int nblocks, cudaStream_t st);
 // copy `nrows` plane rows of `nplanes` planes: dst[i] + dst_row*pitch <- src[i] + src_row*pitch

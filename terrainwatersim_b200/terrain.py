@@ -195,6 +195,36 @@ class Terrain:
     def readback_raw(self, field: int, ptr: int, nbytes: int) -> None:
         self._check(self._lib.tws_readback(self._sim, field, C.c_void_p(ptr), nbytes))
 
+    # ---- renderer hand-off ------------------------------------------------------------------------
+    def publish_packed(self) -> Tuple[int, int]:
+        """Device pointers of the packed TerrainInfo (RGBA32F) and FlowMap (RG16F) level-0 images."""
+        info, flow = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.tws_publish_packed(self._sim, C.byref(info), C.byref(flow)))
+        return int(info.value), int(flow.value)
+
+    def publish_mips(self) -> list:
+        """GenMipMaps of m_terrainData (Terrain.cpp:272-276): builds the chain on the device and
+        returns every level as a (h, w, 4) float32 host array."""
+        base, levels = C.c_void_p(), C.c_int32(0)
+        self._check(self._lib.tws_publish_mips(self._sim, C.byref(base), C.byref(levels)))
+        out = []
+        for l in range(levels.value):
+            w, h, off = C.c_int32(), C.c_int32(), C.c_int64()
+            self._check(self._lib.tws_mip_level_info(self.width, self.rows, l, C.byref(w), C.byref(h), C.byref(off)))
+            a = np.empty((h.value, w.value, 4), np.float32)
+            self._check(self._lib.tws_readback_mip(self._sim, l, a.ctypes.data_as(C.c_void_p), a.nbytes))
+            out.append(a)
+        return out
+
+    def gl_register(self, terrain_info_tex: int, flow_map_tex: int = 0) -> None:
+        self._check(self._lib.tws_gl_register(self._sim, int(terrain_info_tex), int(flow_map_tex)))
+
+    def gl_publish(self) -> None:
+        self._check(self._lib.tws_gl_publish(self._sim))
+
+    def gl_unregister(self) -> None:
+        self._check(self._lib.tws_gl_unregister(self._sim))
+
     # ---- strips ---------------------------------------------------------------------------------
     def halo_export(self) -> bytes:
         h = _abi.TwsHaloHandle()

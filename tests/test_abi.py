@@ -133,3 +133,22 @@ def test_no_fused_multiply_add_in_the_step_kernels(tws):
         assert n_ffma <= 5 * n_rcp + 60, f"{name}: {n_ffma} FFMA for {n_rcp} divisions"
         assert n_rcp > 0 or n_ffma == 0, name
         assert n_call >= 0
+
+
+def test_mip_level_rule_matches_the_reference_texture_wrapper(tws):
+    """tws_mip_levels / tws_mip_level_info are pure host functions (no GPU needed): level count of glEasy
+    Texture.cpp:28-41, glTexStorage2D level sizes, contiguous level offsets."""
+    from oracle.oracle_py import mip_levels
+    lib = tws._abi.load()
+    for W, H in [(1024, 1024), (1, 1), (37, 5), (5, 37), (257, 64), (8192, 8192), (3, 2)]:
+        L = lib.tws_mip_levels(W, H)
+        assert L == mip_levels(W, H)
+        off = 0
+        for l in range(L):
+            w, h, o = C.c_int32(), C.c_int32(), C.c_int64()
+            assert lib.tws_mip_level_info(W, H, l, C.byref(w), C.byref(h), C.byref(o)) == 0
+            assert (w.value, h.value, o.value) == (max(1, W >> l), max(1, H >> l), off)
+            off += w.value * h.value
+        assert lib.tws_mip_level_info(W, H, L, None, None, None) != 0
+        assert lib.tws_mip_level_info(W, H, -1, None, None, None) != 0
+    assert lib.tws_mip_levels(1024, 1024) == 11

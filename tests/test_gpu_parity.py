@@ -363,3 +363,46 @@ def test_step_host_band_pipeline_matches_oracle(tws, oracle_omp, W, H, name, bac
         sim.step_host(None, None, None)                 # outputs are optional
         oracle_omp.step(t, f, v, c, 1)
         assert_state_equal(sim, tws, t, f, v, f"{name} step_host without outputs")
+
+
+@pytest.mark.parametrize("W,H", [(1024, 1024), (300, 200), (37, 5), (5, 37), (257, 64), (1, 1)])
+def test_terrain_info_mip_chain_matches_oracle(tws, oracle, W, H):
+    """Renderer hand-off: TerrainInfo level 0 = (terrain, 0.3, 0.3, water) and the mip chain the
+    reference regenerates after every stepped frame (Terrain.cpp:272-276), against the pinned box filter of
+    oracle_py.mip_chain — every level, bit for bit, after a few steps so that the water channel is live."""
+    from oracle.oracle_py import mip_chain
+    h, d = bumpy(W, H, seed=11)
+    t, f, v = new_state(h, d)
+    c = oracle.derive_consts(float(W), W)
+    oracle.step(t, f, v, c, 3)
+    with make_sim(tws, W, H, 5, 3) as sim:
+        sim.upload(tws.FIELD_TERRAIN, h); sim.upload(tws.FIELD_WATER, d)
+        sim.step(3)
+        got = sim.publish_mips()
+        want = mip_chain(t)
+        assert len(got) == len(want)
+        for l, (g_, w_) in enumerate(zip(got, want)):
+            assert g_.shape == w_.shape, f"level {l}"
+            assert np.array_equal(bits(g_), bits(w_)), f"level {l} differs"
+        # level 0 alone (tws_publish_packed) leaves the rest of the chain unpublished
+        sim.step(1)
+        sim.publish_packed()
+        a = np.empty((max(1, H >> 1), max(1, W >> 1), 4), np.float32)
+        if len(want) > 1:
+            assert sim._lib.tws_readback_mip(sim._sim, 1, a.ctypes.data, a.nbytes) == tws._abi.TWS_ERR_STATE
+
+
+def test_gl_interop_without_a_gl_context_fails_cleanly(tws):
+    """The GL entry points are real (cudaGraphicsGLRegisterImage + mapped-array copies), but the GPU box has no
+    GL context: registering must come back as an error status with a message, never crash; publish before a
+    successful register is a state error; unregister is idempotent."""
+    with make_sim(tws, 64, 64, 2, 1) as sim:
+        with pytest.raises(tws.TwsError) as e:
+            sim.gl_register(1, 2)
+        assert e.value.status in (tws._abi.TWS_ERR_CUDA, tws._abi.TWS_ERR_UNSUPPORTED) and str(e.value)
+        with pytest.raises(tws.TwsError) as e:
+            sim.gl_publish()
+        assert e.value.status == tws._abi.TWS_ERR_STATE
+        sim.gl_unregister(); sim.gl_unregister()
+        sim.step(2)                                           # the sim is still usable
+        assert np.isfinite(sim.total_volume())
