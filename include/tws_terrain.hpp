@@ -56,6 +56,12 @@ class Terrain {
   float SimulationTimeMs() { float ms = 0; check(tws_elapsed_ms(sim_, &ms)); return ms; }   // "Simulation Time" stat, Scene.cpp:341-342
   void Upload(tws_field f, const void* host, size_t bytes) { check(tws_upload(sim_, f, host, bytes)); }
   void Readback(tws_field f, void* host, size_t bytes) { check(tws_readback(sim_, f, host, bytes)); }
+  // Renderer hand-off (Terrain.cpp:272-276,288,323-330): the renderer keeps owning TerrainInfo (RGBA32F, full
+  // mip chain) and FlowMap (RG16F); register their GL names once with the GL context current, publish per frame.
+  void RegisterGLTextures(uint32_t terrainInfoTex, uint32_t flowMapTex) { check(tws_gl_register(sim_, terrainInfoTex, flowMapTex)); }
+  void PublishToGL() { check(tws_gl_publish(sim_)); }
+  // the same images in library-owned device memory: level L of TerrainInfo follows level L-1 (tws_mip_level_info)
+  void* PublishMips(int32_t* levels = nullptr) { void* p = nullptr; check(tws_publish_mips(sim_, &p, levels)); return p; }
   tws_sim* handle() { return sim_; }
 
  private:

@@ -478,7 +478,12 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
     const int sx0 = strip * OX - HX;
     const int ystart = ya - HP;                           // 2K warm-up rows above, 2K feeder rows below
     const int N = (yb - ya) + 2 * HP;
-    const int J = (N + BR - 1) / BR;                      // bands that load rows; band J only finishes the carried ones
+    // Bands of the piece.  The rows a band leaves unfinished (its last 2K, carried into the next band) are in
+    // the last band always feeder rows or rows past the piece (N <= J*BR puts row N-2K at or before the first
+    // carried row J*BR-2K), and a feeder at distance t below the last output row needs only 2K-t half-passes,
+    // which its place in the window gives it — so no further band is needed to finish anything that is kept
+    // (model-checked in tests/test_band_schedule.py).
+    const int J = (N + BR - 1) / BR;
     const bool xedge = sx0 < 0 || sx0 + SXW > g.W;
     const int gx = sx0 + lane * 4;
     const bool st_col = lane * 4 >= HX && lane * 4 < HX + OX && gx < g.pitch;
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
     };
 
 #pragma unroll 1
-    for (int j = 0; j <= J; ++j) {
+    for (int j = 0; j < J; ++j) {
       const int i0 = j * BR;
 #pragma unroll
       for (int q = 0; q < R; ++q) set_row(q, j, i0 + q * NW + warp);
@@ -614,24 +619,26 @@ static int band_sm_count() {
 }
 
 // Guided schedule for `rows` rows of `nstrips` strips on up to `max_groups` warp groups (see BandSched).
-static BandSched band_schedule(int rows, int nstrips, int max_groups, int BR) {
+static BandSched band_schedule(int rows, int nstrips, int max_groups, int BR, int HP) {
   BandSched s{};
   const long long total = (long long)rows * nstrips;
   const int even = (int)((total + max_groups - 1) / max_groups);            // rows per group if the work were split evenly
   // shortest segment: long enough that the 2K warm-up / feeder rows and the extra band amortise (128 rows), but
   // small grids are latency bound and rather use every SM (at least ~4 bands per piece)
   const int smin = std::max(4 * BR, std::min(128, even));
-  int size = std::max(smin, even / 2);
+  // a piece computes rows + 2*HP rows in whole bands: sizes that make that a multiple of BR waste nothing
+  auto whole_bands = [&](int sz) { return std::max(BR, (sz + 2 * HP + BR - 1) / BR * BR) - 2 * HP; };
+  int size = whole_bands(std::max(smin, even / 2));
   int y = 0, seg = 0, l = 0;
   while (y < rows) {
     const int rem = rows - y;
-    const bool rest = size <= smin || l == BandSched::MAXLEV - 1;
+    const bool rest = size <= whole_bands(smin) || l == BandSched::MAXLEV - 1;
     const int n = rest ? (rem + size - 1) / size : std::max(1, rem / 2 / size);   // about half of what is left per level
     s.seg0[l] = seg; s.y0[l] = y; s.size[l] = size;
     seg += n;
     y += (int)std::min<long long>(rem, (long long)n * size);
     ++l;
-    size = std::max(smin, size / 2);
+    size = whole_bands(std::max(smin, size / 2));
   }
   s.nlev = l;
   s.rows = rows;
@@ -641,7 +648,7 @@ static BandSched band_schedule(int rows, int nstrips, int max_groups, int BR) {
 
 template <int K, bool EXT>
 static cudaError_t launch_band_k(const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
-                                 cudaStream_t st, uint32_t* sched) {
+                                 cudaStream_t st, uint32_t* sched, int cta_budget) {
   using C = typename BandCfgFor<K>::type;
   if (C::SXW != stream_strip_width()) return cudaErrorInvalidValue;      // ring and band kernels share the row descriptors
   static bool attr_set[64] = {};
@@ -662,8 +669,11 @@ static cudaError_t launch_band_k(const Geom& g, const Planes& p, const TmaSet& t
   out.v = p.v + row0_off;
   const int nstrips = (g.W + C::OX - 1) / C::OX;
   // one persistent CTA per SM (fewer when there are fewer pieces than warp groups)
-  const int sms = band_sm_count();
-  const BandSched sch = band_schedule(lr1 - lr0, nstrips, sms * C::NGRP, C::BR);
+  // cta_budget > 0: use at most that many SMs, < 0: leave that many free (strips: the edge launches of the other
+  // stream run beside the interior launch instead of behind it)
+  const int all_sms = band_sm_count();
+  const int sms = cta_budget > 0 ? std::min(cta_budget, all_sms) : std::max(1, all_sms + cta_budget);
+  const BandSched sch = band_schedule(lr1 - lr0, nstrips, sms * C::NGRP, C::BR, C::HP);
   const int want = (sch.npieces + C::NGRP - 1) / C::NGRP;
   const int grid = want < 1 ? 1 : (want < sms ? want : sms);
   const int bias = g.has_up ? TWS_HALO_ROWS : 0;
@@ -672,13 +682,13 @@ static cudaError_t launch_band_k(const Geom& g, const Planes& p, const TmaSet& t
 }
 
 cudaError_t launch_band(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
-                        cudaStream_t st, uint32_t* sched) {
+                        cudaStream_t st, uint32_t* sched, int cta_budget) {
   const bool ext = c.ext_sources != 0;
   switch (K) {
-    case 1: return ext ? launch_band_k<1, true>(g, p, tma, src, c, lr0, lr1, st, sched) : launch_band_k<1, false>(g, p, tma, src, c, lr0, lr1, st, sched);
-    case 2: return ext ? launch_band_k<2, true>(g, p, tma, src, c, lr0, lr1, st, sched) : launch_band_k<2, false>(g, p, tma, src, c, lr0, lr1, st, sched);
-    case 3: return ext ? launch_band_k<3, true>(g, p, tma, src, c, lr0, lr1, st, sched) : launch_band_k<3, false>(g, p, tma, src, c, lr0, lr1, st, sched);
-    case 4: return ext ? launch_band_k<4, true>(g, p, tma, src, c, lr0, lr1, st, sched) : launch_band_k<4, false>(g, p, tma, src, c, lr0, lr1, st, sched);
+    case 1: return ext ? launch_band_k<1, true>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget) : launch_band_k<1, false>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget);
+    case 2: return ext ? launch_band_k<2, true>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget) : launch_band_k<2, false>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget);
+    case 3: return ext ? launch_band_k<3, true>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget) : launch_band_k<3, false>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget);
+    case 4: return ext ? launch_band_k<4, true>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget) : launch_band_k<4, false>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -546,9 +546,9 @@ static cudaError_t launch_stream_k(const Geom& g, const Planes& p, const TmaSet&
 
 // impl: 0 = ring kernel (per-row barriers), 1 = band kernel (CTA-synchronous bands)
 cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
-                          cudaStream_t st, int impl, uint32_t* sched) {
+                          cudaStream_t st, int impl, uint32_t* sched, int cta_budget) {
   const bool ext = c.ext_sources != 0;
-  if (impl == 1) return launch_band(K, g, p, tma, src, c, lr0, lr1, st, sched);
+  if (impl == 1) return launch_band(K, g, p, tma, src, c, lr0, lr1, st, sched, cta_budget);
   switch (K) {
     case 1: return ext ? launch_stream_k<1, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<1, false>(g, p, tma, src, c, lr0, lr1, st);
     case 2: return ext ? launch_stream_k<2, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<2, false>(g, p, tma, src, c, lr0, lr1, st);

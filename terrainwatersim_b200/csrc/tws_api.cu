@@ -219,6 +219,11 @@ tws_status post_and_count(tws_sim* s, cudaStream_t st) {
 // One block of k steps of the row-streaming pipeline.  A strip runs the rows that neither depend on
 // a halo nor are pushed to a neighbour (all but the outer TWS_HALO_ROWS) on the main stream and the
 // two edge bands on the edge stream behind the neighbours' flags, exactly like the tile engine.
+// The band kernel is persistent (one CTA per SM, each as large as an SM): edge launches queued behind a full-width
+// interior launch would only start when it drains.  A strip therefore leaves kEdgeSMs SMs to the edge stream — the two
+// edge bands are ~1 % of a strip's rows, 2 of 148 SMs is 1.4 % — so edge compute, halo push and flag post overlap the
+// interior instead of following it.
+constexpr int kEdgeSMs = 2;
 tws_status run_block_stream(tws_sim* s, int k) {
   const Geom& g = s->geom;
   const bool strip = g.has_up || g.has_down;
@@ -236,13 +241,13 @@ tws_status run_block_stream(tws_sim* s, int k) {
   const int i0 = e_top, i1 = g.rows - e_bot;
   TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));
   if (i1 > i0) {
-    TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i0, i1, s->st_main, stream_impl(s), s->ctrl->sched_main));
+    TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i0, i1, s->st_main, stream_impl(s), s->ctrl->sched_main, -kEdgeSMs));
     s->launches += 1;
   }
   TWS_CUDA(s, cudaStreamWaitEvent(s->st_edge, s->ev_main, 0));
   TWS_CUDA(s, launch_wait_flags(s->ctrl, g.has_up, g.has_down, s->epoch, s->st_edge)); s->launches++;
-  if (e_top > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, e_top, s->st_edge, stream_impl(s), s->ctrl->sched_edge)); s->launches++; }
-  if (e_bot > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i1, g.rows, s->st_edge, stream_impl(s), s->ctrl->sched_edge)); s->launches++; }
+  if (e_top > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, e_top, s->st_edge, stream_impl(s), s->ctrl->sched_edge, kEdgeSMs)); s->launches++; }
+  if (e_bot > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i1, g.rows, s->st_edge, stream_impl(s), s->ctrl->sched_edge, kEdgeSMs)); s->launches++; }
   r = push_edges(s, 1 - src, false, s->st_edge); if (r) return r;
   r = post_and_count(s, s->st_edge); if (r) return r;
   TWS_CUDA(s, cudaEventRecord(s->ev_edge, s->st_edge));

@@ -23,6 +23,13 @@ int main(int argc, char** argv) {
       const uint32_t n = t.PerformSimulationStep(0.05);
       t.Sync();
       std::printf("steps=%u v0=%.6f v1=%.6f ms=%.4f\n", n, v0, t.TotalVolume(), t.SimulationTimeMs());
+      int32_t levels = 0;
+      const void* chain = t.PublishMips(&levels);          // GenMipMaps of TerrainInfo, Terrain.cpp:272-276
+      int32_t lw = 0, lh = 0; int64_t off = 0;
+      tws_mip_level_info(128, 128, levels - 1, &lw, &lh, &off);
+      std::printf("mips=%d chain=%s last=%dx%d@%lld\n", levels, chain ? "ok" : "null", lw, lh, (long long)off);
+      try { t.RegisterGLTextures(1, 2); std::printf("gl=registered\n"); }     // no GL context on a compute box: a clean error
+      catch (const tws::Error& e) { std::printf("gl=error %d\n", (int)e.status); }
     } catch (const tws::Error& e) {
       std::printf("error %d: %s\n", (int)e.status, e.what());
       return 2;

@@ -44,7 +44,7 @@ def run_piece(NW, R, K, rows_out, seed):
     def exact(i, s):                           # is row i after half-pass s an exact value (cone inside the loaded rows)?
         return 0 <= i < N and i - s >= 0 and i + s <= N - 1
 
-    for j in range(J + 1):
+    for j in range(J):                         # no extra band: what the last band leaves unfinished is never kept
         i0 = j * BR
         # ---- half-pass 0: load + publish H (after the wait for the previous band's last arrive) ----
         cur = {}                               # (w, q) -> (band index, band row) the register set currently belongs to

@@ -283,6 +283,7 @@ def test_cxx_host_wrapper_runs(tws, tmp_path):
     out = subprocess.run([str(exe), "run"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "steps=2" in out.stdout          # 0.05 s at 60 steps/s -> (uint)(0.05/0.016667) = 2 (Terrain.cpp:243)
+    assert "mips=8 chain=ok last=1x1@" in out.stdout and "gl=" in out.stdout      # 128 -> 8 levels (Texture.cpp:28-41)
 
 
 # ---- full-size properties (BASELINE config 3 grid: 8192 x 8192) ------------------------------------
