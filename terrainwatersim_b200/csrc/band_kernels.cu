@@ -37,6 +37,8 @@
 #include "cell_math.cuh"
 
 #include <algorithm>
+#include <climits>
+#include <cstdlib>
 
 namespace tws {
 
@@ -75,10 +77,11 @@ struct BandRow {       // per-row context (the lane's column offset and store ma
 // feeder rows amortise.  Piece p = (segment p / nstrips, strip p % nstrips): the pieces in flight at any
 // time are the same rows of neighbouring strips, which keeps their shared halo columns in L2.
 struct BandSched {
-  static constexpr int MAXLEV = 12;
-  int nlev, npieces, rows;
+  static constexpr int MAXLEV = 14;
+  int nlev, npieces;
   int seg0[MAXLEV];    // first segment of level l
   int y0[MAXLEV];      // first row (relative to lr0) of level l
+  int yend[MAXLEV];    // end row of level l
   int size[MAXLEV];    // rows per segment of level l (the last segment of a level may be shorter)
 };
 
@@ -124,6 +127,17 @@ struct GroupSync {
   }
 };
 
+// Strips: an output row that a neighbouring strip needs as halo is stored a second time, straight into that
+// neighbour's halo row (peer store over NVLink).  y: own local row; go: the element offset used for the own store.
+__device__ __forceinline__ void push_flux(const BandEdge& e, int y, size_t go, const float4& fx, const float4& fy, const float4& fz, const float4& fw) {
+  if (y < e.up_end) { st4(e.up[1] + go, fx); st4(e.up[2] + go, fy); st4(e.up[3] + go, fz); st4(e.up[4] + go, fw); }
+  if (y >= e.down_begin) { st4(e.down[1] + go, fx); st4(e.down[2] + go, fy); st4(e.down[3] + go, fz); st4(e.down[4] + go, fw); }
+}
+__device__ __forceinline__ void push_depth(const BandEdge& e, int y, size_t go, const float4& d) {
+  if (y < e.up_end) st4(e.up[0] + go, d);
+  if (y >= e.down_begin) st4(e.down[0] + go, d);
+}
+
 // flowUpdate.comp:34-62 for the lane's 4 cells of each of its R rows.  Reads the neighbour rows' water
 // level, leaves the new outflow in registers, publishes its +-Y components; LAST also stores the flux
 // planes to HBM.  up / dn / me: 32-bit shared addresses of this lane's group in plane 0 of the slots.
@@ -134,7 +148,7 @@ template <int R, int SXW, bool EDGE, bool LAST>
 __device__ __forceinline__ void band_flux(GroupSync& sy, const uint32_t (&up)[R], const uint32_t (&dn)[R], const uint32_t (&me)[R],
                                           const float4 (&h)[R], const float4 (&d)[R], float4 (&fx)[R], float4 (&fy)[R], float4 (&fz)[R],
                                           float4 (&fw)[R], const BandRow (&rc)[R], const int gx, const bool st_col, const FusedOut& out,
-                                          const Geom& g, const StepConsts& c) {
+                                          const Geom& g, const StepConsts& c, const BandEdge& edge) {
   float4 HC[R], HU[R], HD[R];
   float HL[R], HR[R];
   float total[R][4], scale[R][4];
@@ -269,6 +283,7 @@ __device__ __forceinline__ void band_flux(GroupSync& sy, const uint32_t (&up)[R]
     }
     if (LAST && rc[q].store && st_col && !TWS_DBG_NOSTORE) {
       st4(out.F[0] + rc[q].go, fx[q]); st4(out.F[1] + rc[q].go, fy[q]); st4(out.F[2] + rc[q].go, fz[q]); st4(out.F[3] + rc[q].go, fw[q]);
+      if (edge.nlev_edge) push_flux(edge, rc[q].gy - g.row0, rc[q].go, fx[q], fy[q], fz[q], fw[q]);
     }
   }
 }
@@ -294,7 +309,7 @@ template <int R, int SXW, bool EDGE, bool LAST, bool EXT>
 __device__ __forceinline__ void band_depth(GroupSync& sy, const uint32_t (&up)[R], const uint32_t (&dn)[R], const uint32_t (&me)[R],
                                            const float4 (&h)[R], float4 (&d)[R], const float4 (&fx)[R], const float4 (&fy)[R],
                                            const float4 (&fz)[R], const float4 (&fw)[R], const BandRow (&rc)[R], const int gx,
-                                           const bool st_col, const FusedOut& out, const Geom& g, const StepConsts& c) {
+                                           const bool st_col, const FusedOut& out, const Geom& g, const StepConsts& c, const BandEdge& edge) {
   float4 iy1[R], iy0[R];
   float l[R], r[R];
 #pragma unroll
@@ -357,6 +372,7 @@ __device__ __forceinline__ void band_depth(GroupSync& sy, const uint32_t (&up)[R
         upk(sub2(sub2(hi2(iy1[q]), hi2(fz[q])), sub2(hi2(iy0[q]), hi2(fw[q]))), vy2, vy3);
         if (rc[q].store && st_col && !TWS_DBG_NOSTORE) {
           st4(out.d + rc[q].go, nd[q]);
+          if (edge.nlev_edge) push_depth(edge, rc[q].gy - g.row0, rc[q].go, nd[q]);
           *reinterpret_cast<uint4*>(out.v + rc[q].go) =
               make_uint4(pack_half2(vx[q][0], vy0), pack_half2(vx[q][1], vy1), pack_half2(vx[q][2], vy2), pack_half2(vx[q][3], vy3));
         }
@@ -394,8 +410,22 @@ __device__ __forceinline__ void band_depth(GroupSync& sy, const uint32_t (&up)[R
     for (int q = 0; q < R; ++q)
       if (rc[q].store && st_col && !TWS_DBG_NOSTORE) {
         st4(out.d + rc[q].go, make_float4(nds[q][0], nds[q][1], nds[q][2], nds[q][3]));
+        if (edge.nlev_edge) push_depth(edge, rc[q].gy - g.row0, rc[q].go, make_float4(nds[q][0], nds[q][1], nds[q][2], nds[q][3]));
         *reinterpret_cast<uint4*>(out.v + rc[q].go) = make_uint4(nvs[q][0], nvs[q][1], nvs[q][2], nvs[q][3]);
       }
+  }
+}
+
+// Poll a flag in the own control block until the neighbour has published epoch >= value.  Bounded: after ~20 s
+// the wait gives up and raises ctrl->error, so a dead peer cannot hang the GPU.
+__device__ __noinline__ void band_wait_flag(const volatile uint32_t* flag, uint32_t value, uint32_t* error) {
+  if ((int32_t)(*flag - value) >= 0) return;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while ((int32_t)(*flag - value) < 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 20000000000ull) { *error = 1u; return; }
+    __nanosleep(100);
   }
 }
 
@@ -403,6 +433,7 @@ template <class C, bool EXT>
 __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_constant__ CUtensorMap tm_h,
                                                              const __grid_constant__ CUtensorMap tm_s,
                                                              const __grid_constant__ BandSched sch,
+                                                             const __grid_constant__ BandEdge edge,
                                                              FusedOut out, Geom g, StepConsts c, int lr0, int lr1, int nstrips,
                                                              int tma_y_bias, uint32_t* sched) {
   constexpr int K = C::K, NW = C::NW, R = C::R, BR = C::BR, SXW = C::SXW, HX = C::HX, OX = C::OX, HP = C::HP, LAND = C::LAND, XROW = C::XROW;
@@ -463,18 +494,34 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
 
 #pragma unroll 1
   while (piece < sch.npieces) {
-    // fetch the piece after this one now: the atomic's round trip hides behind the whole piece; the group reads
-    // the slot after the piece's barriers (release / acquire), and the two slots alternate so that the next
-    // write cannot overtake a reader
+    // fetch the piece after this one now: the atomic's round trip hides behind the first TMA load of the piece (any
+    // later and the fetching warp — and with it the group — waits for it: ptxas aggregates the atomic over the warp
+    // and broadcasts the result with a shuffle right behind it, so the value cannot be left in flight); the group
+    // reads the slot behind the piece's barriers (release / acquire), and the two slots alternate so that the next
+    // write cannot overtake a reader.  Committing one piece ahead is harmless because pieces shrink along the list:
+    // a group never holds more than a fraction of its fair share — which is also why a strip's tiny edge pieces come
+    // LAST in the list (first, every group would fetch twice within microseconds and end up holding two long pieces).
     if (sched && warp == 0 && lane == 0) next_piece[grp][pp] = nvcta + (int)atomicAdd(sched, 1u);
     const int seg = piece / nstrips, strip = piece - seg * nstrips;
     int lev = 0;
 #pragma unroll 1
     while (lev + 1 < sch.nlev && seg >= sch.seg0[lev + 1]) ++lev;
-    const int lev_end = lev + 1 < sch.nlev ? sch.y0[lev + 1] : sch.rows;
+    const int lev_end = sch.yend[lev];
     const int ya_rel = sch.y0[lev] + (seg - sch.seg0[lev]) * sch.size[lev];
     const int ya = lr0 + ya_rel;
     const int yb = lr0 + (ya_rel + sch.size[lev] < lev_end ? ya_rel + sch.size[lev] : lev_end);
+    const bool edge_piece = edge.nlev_edge != 0 && lev >= edge.lev_edge0;
+    if (edge_piece) {
+      // the halo rows this piece reads were stored by the neighbour's previous block: wait for its flag (it is
+      // normally long there), then order this warp's loads — generic and TMA — behind the observation
+      if (lane == 0) {
+        if (edge.wait_up != nullptr && ya - HP < 0) band_wait_flag(edge.wait_up, edge.wait_value, edge.error);
+        if (edge.wait_down != nullptr && yb + HP > g.rows) band_wait_flag(edge.wait_down, edge.wait_value, edge.error);
+        __threadfence_system();
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      __syncwarp();
+    }
     const int sx0 = strip * OX - HX;
     const int ystart = ya - HP;                           // 2K warm-up rows above, 2K feeder rows below
     const int N = (yb - ya) + 2 * HP;
@@ -569,18 +616,31 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
 #pragma unroll 1
       for (int lv = 1; lv < K; ++lv) {
         if (2 * lv - 1 == swap_at) swap_rows(j);
-        if (plain) band_flux<R, SXW, false, false>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-        else band_flux<R, SXW, true, false>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+        if (plain) band_flux<R, SXW, false, false>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
+        else band_flux<R, SXW, true, false>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
         if (2 * lv == swap_at) swap_rows(j);
-        if (plain) band_depth<R, SXW, false, false, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-        else band_depth<R, SXW, true, false, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+        if (plain) band_depth<R, SXW, false, false, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
+        else band_depth<R, SXW, true, false, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
       }
       if (HP - 1 == swap_at) swap_rows(j);
-      if (plain) band_flux<R, SXW, false, true>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-      else band_flux<R, SXW, true, true>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+      if (plain) band_flux<R, SXW, false, true>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
+      else band_flux<R, SXW, true, true>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
       if (HP == swap_at) swap_rows(j);
-      if (plain) band_depth<R, SXW, false, true, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
-      else band_depth<R, SXW, true, true, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c);
+      if (plain) band_depth<R, SXW, false, true, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
+      else band_depth<R, SXW, true, true, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
+    }
+    if (edge_piece) {
+      // every lane's stores into the neighbours' halos are visible system-wide before this warp counts itself done;
+      // the warp that completes the last edge piece of the launch publishes the new epoch to the neighbours
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0 && atomicAdd(sched + 2, 1u) == edge.n_edge_warps - 1u) {
+        sched[2] = 0u;
+        __threadfence_system();
+        if (edge.post_up != nullptr) *edge.post_up = edge.post_value;
+        if (edge.post_down != nullptr) *edge.post_down = edge.post_value;
+        __threadfence_system();
+      }
     }
     piece = sched ? *(volatile int*)&next_piece[grp][pp] : piece + nvcta;
     pp ^= 1;
@@ -618,37 +678,45 @@ static int band_sm_count() {
   return cached[dev & 63] > 0 ? cached[dev & 63] : 148;
 }
 
-// Guided schedule for `rows` rows of `nstrips` strips on up to `max_groups` warp groups (see BandSched).
-static BandSched band_schedule(int rows, int nstrips, int max_groups, int BR, int HP) {
-  BandSched s{};
+// Guided schedule (see BandSched): appends levels covering rows [y_begin, y_end) of `nstrips` strips for up to
+// `max_groups` warp groups to `s`; `seg` is the running segment count.
+static void band_schedule_rows(BandSched& s, int& seg, int y_begin, int y_end, int nstrips, int max_groups, int BR, int HP) {
+  const int rows = y_end - y_begin;
+  if (rows <= 0) return;
   const long long total = (long long)rows * nstrips;
   const int even = (int)((total + max_groups - 1) / max_groups);            // rows per group if the work were split evenly
-  // shortest segment: long enough that the 2K warm-up / feeder rows and the extra band amortise (128 rows), but
-  // small grids are latency bound and rather use every SM (at least ~4 bands per piece)
+  // shortest segment: long enough that the 2K warm-up / feeder rows amortise (128 rows), but small grids are
+  // latency bound and rather use every SM (at least ~4 bands per piece)
   const int smin = std::max(4 * BR, std::min(128, even));
   // a piece computes rows + 2*HP rows in whole bands: sizes that make that a multiple of BR waste nothing
   auto whole_bands = [&](int sz) { return std::max(BR, (sz + 2 * HP + BR - 1) / BR * BR) - 2 * HP; };
   int size = whole_bands(std::max(smin, even / 2));
-  int y = 0, seg = 0, l = 0;
-  while (y < rows) {
-    const int rem = rows - y;
-    const bool rest = size <= whole_bands(smin) || l == BandSched::MAXLEV - 1;
+  int y = y_begin;
+  while (y < y_end) {
+    const int l = s.nlev;
+    const int rem = y_end - y;
+    const bool rest = size <= whole_bands(smin) || l >= BandSched::MAXLEV - 3;      // two levels stay free for a strip's edge bands
     const int n = rest ? (rem + size - 1) / size : std::max(1, rem / 2 / size);   // about half of what is left per level
-    s.seg0[l] = seg; s.y0[l] = y; s.size[l] = size;
+    const int cover = (int)std::min<long long>(rem, (long long)n * size);
+    s.seg0[l] = seg; s.y0[l] = y; s.yend[l] = y + cover; s.size[l] = size;
     seg += n;
-    y += (int)std::min<long long>(rem, (long long)n * size);
-    ++l;
+    y += cover;
+    s.nlev = l + 1;
     size = whole_bands(std::max(smin, size / 2));
   }
-  s.nlev = l;
-  s.rows = rows;
-  s.npieces = seg * nstrips;
-  return s;
+}
+// one level holding a single segment [y_begin, y_end): an edge band of a strip
+static void band_schedule_one(BandSched& s, int& seg, int y_begin, int y_end) {
+  if (y_end <= y_begin) return;
+  const int l = s.nlev;
+  s.seg0[l] = seg; s.y0[l] = y_begin; s.yend[l] = y_end; s.size[l] = y_end - y_begin;
+  seg += 1;
+  s.nlev = l + 1;
 }
 
 template <int K, bool EXT>
 static cudaError_t launch_band_k(const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
-                                 cudaStream_t st, uint32_t* sched, int cta_budget) {
+                                 cudaStream_t st, uint32_t* sched, int cta_budget, const BandEdge* edge, int e_top, int e_bot) {
   using C = typename BandCfgFor<K>::type;
   if (C::SXW != stream_strip_width()) return cudaErrorInvalidValue;      // ring and band kernels share the row descriptors
   static bool attr_set[64] = {};
@@ -661,6 +729,7 @@ static cudaError_t launch_band_k(const Geom& g, const Planes& p, const TmaSet& t
     attr_set[dev & 63] = true;
   }
   if (lr1 <= lr0) return cudaSuccess;
+  if (edge != nullptr && sched == nullptr) return cudaErrorInvalidValue;
   const int dst = 1 - src;
   const size_t row0_off = (size_t)TWS_HALO_ROWS * g.pitch;
   FusedOut out;
@@ -668,27 +737,44 @@ static cudaError_t launch_band_k(const Geom& g, const Planes& p, const TmaSet& t
   for (int i = 0; i < 4; ++i) out.F[i] = p.F[dst][i] + row0_off;
   out.v = p.v + row0_off;
   const int nstrips = (g.W + C::OX - 1) / C::OX;
-  // one persistent CTA per SM (fewer when there are fewer pieces than warp groups)
-  // cta_budget > 0: use at most that many SMs, < 0: leave that many free (strips: the edge launches of the other
-  // stream run beside the interior launch instead of behind it)
+  // one persistent CTA per SM (fewer when there are fewer pieces than warp groups); cta_budget > 0: at most that
+  // many CTAs, < 0: leave that many SMs free
   const int all_sms = band_sm_count();
   const int sms = cta_budget > 0 ? std::min(cta_budget, all_sms) : std::max(1, all_sms + cta_budget);
-  const BandSched sch = band_schedule(lr1 - lr0, nstrips, sms * C::NGRP, C::BR, C::HP);
+  BandSched sch{};
+  BandEdge ed{};
+  int seg = 0;
+  const int rel1 = lr1 - lr0;                            // schedule rows are relative to lr0
+  if (edge != nullptr) {
+    // a strip's block: the interior, then the edge bands — tiny pieces that fill the tail of the launch; the
+    // neighbours need them only for THEIR edge pieces at the end of their next block
+    ed = *edge;
+    band_schedule_rows(sch, seg, e_top, rel1 - e_bot, nstrips, sms * C::NGRP, C::BR, C::HP);
+    ed.lev_edge0 = sch.nlev;
+    const int seg_i = seg;
+    band_schedule_one(sch, seg, 0, e_top);
+    band_schedule_one(sch, seg, rel1 - e_bot, rel1);
+    ed.nlev_edge = sch.nlev - ed.lev_edge0;
+    ed.n_edge_warps = (unsigned)(seg - seg_i) * (unsigned)nstrips * (unsigned)C::NW;
+  } else {
+    band_schedule_rows(sch, seg, 0, rel1, nstrips, sms * C::NGRP, C::BR, C::HP);
+  }
+  sch.npieces = seg * nstrips;
   const int want = (sch.npieces + C::NGRP - 1) / C::NGRP;
   const int grid = want < 1 ? 1 : (want < sms ? want : sms);
   const int bias = g.has_up ? TWS_HALO_ROWS : 0;
-  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], sch, out, g, c, lr0, lr1, nstrips, bias, sched);
+  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], sch, ed, out, g, c, lr0, lr1, nstrips, bias, sched);
   return cudaGetLastError();
 }
 
 cudaError_t launch_band(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
-                        cudaStream_t st, uint32_t* sched, int cta_budget) {
+                        cudaStream_t st, uint32_t* sched, int cta_budget, const BandEdge* edge, int e_top, int e_bot) {
   const bool ext = c.ext_sources != 0;
   switch (K) {
-    case 1: return ext ? launch_band_k<1, true>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget) : launch_band_k<1, false>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget);
-    case 2: return ext ? launch_band_k<2, true>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget) : launch_band_k<2, false>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget);
-    case 3: return ext ? launch_band_k<3, true>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget) : launch_band_k<3, false>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget);
-    case 4: return ext ? launch_band_k<4, true>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget) : launch_band_k<4, false>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget);
+    case 1: return ext ? launch_band_k<1, true>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget, edge, e_top, e_bot) : launch_band_k<1, false>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget, edge, e_top, e_bot);
+    case 2: return ext ? launch_band_k<2, true>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget, edge, e_top, e_bot) : launch_band_k<2, false>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget, edge, e_top, e_bot);
+    case 3: return ext ? launch_band_k<3, true>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget, edge, e_top, e_bot) : launch_band_k<3, false>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget, edge, e_top, e_bot);
+    case 4: return ext ? launch_band_k<4, true>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget, edge, e_top, e_bot) : launch_band_k<4, false>(g, p, tma, src, c, lr0, lr1, st, sched, cta_budget, edge, e_top, e_bot);
     default: return cudaErrorInvalidValue;
   }
 }

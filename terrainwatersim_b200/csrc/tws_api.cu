@@ -7,6 +7,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -219,11 +220,50 @@ tws_status post_and_count(tws_sim* s, cudaStream_t st) {
 // One block of k steps of the row-streaming pipeline.  A strip runs the rows that neither depend on
 // a halo nor are pushed to a neighbour (all but the outer TWS_HALO_ROWS) on the main stream and the
 // two edge bands on the edge stream behind the neighbours' flags, exactly like the tile engine.
-// The band kernel is persistent (one CTA per SM, each as large as an SM): edge launches queued behind a full-width
-// interior launch would only start when it drains.  A strip therefore leaves kEdgeSMs SMs to the edge stream — the two
-// edge bands are ~1 % of a strip's rows, 2 of 148 SMs is 1.4 % — so edge compute, halo push and flag post overlap the
-// interior instead of following it.
-constexpr int kEdgeSMs = 2;
+// One block of k steps of a strip with the band kernel: ONE launch.  The edge bands are the first pieces of its
+// work list; their warps wait for the neighbours' flags, push every output row into the neighbours' halo rows as they
+// store it and post the new epoch when the last edge piece is done — all while the other warp groups of the same
+// launch work on interior pieces (BandEdge, band_kernels.cu).  No edge stream, no copy kernel, no flag kernels.
+tws_status run_block_band_strip(tws_sim* s, int k) {
+  const Geom& g = s->geom;
+  const int src = s->cur, dst = 1 - src;
+  const int P = TWS_HALO_ROWS;
+  int e_top = g.has_up ? P : 0, e_bot = g.has_down ? P : 0;
+  if (e_top + e_bot >= g.rows) { e_top = g.rows; e_bot = 0; }
+  BandEdge ed{};
+  ed.wait_up = g.has_up ? &s->ctrl->flag_from_up : nullptr;
+  ed.wait_down = g.has_down ? &s->ctrl->flag_from_down : nullptr;
+  ed.wait_value = s->epoch;
+  ed.error = &s->ctrl->error;
+  s->epoch += 1;
+  ed.post_up = s->up.present ? &s->up.ctrl->flag_from_down : nullptr;
+  ed.post_down = s->down.present ? &s->down.ctrl->flag_from_up : nullptr;
+  ed.post_value = s->epoch;
+  ed.up_end = s->up.present ? std::min(P, g.rows) : 0;
+  ed.down_begin = s->down.present ? std::max(0, g.rows - P) : INT32_MAX;
+  auto peer_planes = [&](const Peer& peer, long long row_shift, float* (&out)[5]) {
+    // own row y (element offset y * pitch from local row 0) -> peer plane row y + row_shift
+    out[0] = peer.planes.d[dst] + row_shift * g.pitch;
+    for (int i = 0; i < 4; ++i) out[1 + i] = peer.planes.F[dst][i] + row_shift * g.pitch;
+  };
+  if (s->up.present) peer_planes(s->up, (long long)TWS_HALO_ROWS + s->up.rows, ed.up);          // my top rows -> its bottom halo
+  if (s->down.present) peer_planes(s->down, (long long)TWS_HALO_ROWS - g.rows, ed.down);        // my bottom rows -> its top halo
+  static const int dbg = [] { const char* e = getenv("TWS_EDGE_DEBUG"); return e ? atoi(e) : 0; }();   // timing experiments only
+  if (dbg & 1) { ed.wait_up = nullptr; ed.wait_down = nullptr; }
+  if (dbg & 2) { ed.up_end = 0; ed.down_begin = INT32_MAX; }
+  if (dbg & 4) { ed.post_up = nullptr; ed.post_down = nullptr; }
+  TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));          // a tws_halo_refresh on the edge stream comes first
+  TWS_CUDA(s, launch_band(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, g.rows, s->st_main, s->ctrl->sched_main, 0, &ed, e_top, e_bot));
+  s->launches += 1;
+  TWS_CUDA(s, cudaEventRecord(s->ev_main, s->st_main));
+  s->cur = dst;
+  return TWS_OK;
+}
+
+// One block of k steps of the row-streaming pipeline.  A strip runs the rows that neither depend on
+// a halo nor are pushed to a neighbour (all but the outer TWS_HALO_ROWS) on the main stream and the
+// two edge bands on the edge stream behind the neighbours' flags, exactly like the tile engine
+// (ring kernel; the band kernel does the whole block in one launch, see above).
 tws_status run_block_stream(tws_sim* s, int k) {
   const Geom& g = s->geom;
   const bool strip = g.has_up || g.has_down;
@@ -236,18 +276,19 @@ tws_status run_block_stream(tws_sim* s, int k) {
     s->cur = 1 - src;
     return TWS_OK;
   }
+  if (stream_impl(s) == 1) return run_block_band_strip(s, k);
   int e_top = g.has_up ? TWS_HALO_ROWS : 0, e_bot = g.has_down ? TWS_HALO_ROWS : 0;
   if (e_top + e_bot >= g.rows) { e_top = g.rows; e_bot = 0; }
   const int i0 = e_top, i1 = g.rows - e_bot;
   TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));
   if (i1 > i0) {
-    TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i0, i1, s->st_main, stream_impl(s), s->ctrl->sched_main, -kEdgeSMs));
+    TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i0, i1, s->st_main, stream_impl(s), s->ctrl->sched_main));
     s->launches += 1;
   }
   TWS_CUDA(s, cudaStreamWaitEvent(s->st_edge, s->ev_main, 0));
   TWS_CUDA(s, launch_wait_flags(s->ctrl, g.has_up, g.has_down, s->epoch, s->st_edge)); s->launches++;
-  if (e_top > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, e_top, s->st_edge, stream_impl(s), s->ctrl->sched_edge, kEdgeSMs)); s->launches++; }
-  if (e_bot > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i1, g.rows, s->st_edge, stream_impl(s), s->ctrl->sched_edge, kEdgeSMs)); s->launches++; }
+  if (e_top > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, e_top, s->st_edge, stream_impl(s), s->ctrl->sched_edge)); s->launches++; }
+  if (e_bot > 0) { TWS_CUDA(s, launch_stream(k, g, s->planes, s->tma_stream[src], src, s->consts, i1, g.rows, s->st_edge, stream_impl(s), s->ctrl->sched_edge)); s->launches++; }
   r = push_edges(s, 1 - src, false, s->st_edge); if (r) return r;
   r = post_and_count(s, s->st_edge); if (r) return r;
   TWS_CUDA(s, cudaEventRecord(s->ev_edge, s->st_edge));

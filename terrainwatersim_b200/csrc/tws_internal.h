@@ -33,8 +33,9 @@ struct Control {
   alignas(128) uint32_t error;       // set by the wait kernel on timeout
   // Piece counters of the band kernel's dynamic schedule, {next piece, groups done}: one pair per stream
   // that launches step kernels (launches on one stream are ordered, the pair is re-armed by the kernel itself).
-  alignas(128) uint32_t sched_main[2];
-  alignas(128) uint32_t sched_edge[2];
+  // sched_*[2] counts the warps that have finished an edge piece of a strip launch (the last one posts the flags).
+  alignas(128) uint32_t sched_main[4];
+  alignas(128) uint32_t sched_edge[4];
 };
 
 struct StepConsts {
@@ -67,6 +68,27 @@ struct TmaSet { CUtensorMap m[6]; };
 
 struct KernelStats { uint64_t launches = 0; };
 
+// Strips, band kernel: ONE launch per block does the halo exchange itself.  Its last pieces are the edge rows:
+// their warps wait for the neighbours' flags (local polling), compute, store every output row also into the
+// neighbour's halo rows (peer stores over NVLink), and the warp that finishes the last edge piece posts the new
+// epoch in the neighbours' control blocks — while the other warp groups are still working on interior pieces.
+struct BandEdge {
+  int nlev_edge;                        // levels of the schedule that are edge pieces (0: not a strip launch) ...
+  int lev_edge0;                        // ... and the first of them (they are the last levels of the work list)
+  unsigned n_edge_warps;                // warps that will finish an edge piece in this launch
+  const volatile uint32_t* wait_up;     // own control block: flag written by the strip above / below (nullptr: none)
+  const volatile uint32_t* wait_down;
+  uint32_t wait_value;
+  uint32_t* error;                      // own control block: raised when a wait times out
+  volatile uint32_t* post_up;           // neighbours' control blocks
+  volatile uint32_t* post_down;
+  uint32_t post_value;
+  int up_end;                           // own rows y < up_end are also stored into the upper neighbour's bottom halo
+  int down_begin;                       // own rows y >= down_begin into the lower neighbour's top halo
+  float* up[5];                         // d, F x4 of the neighbour, offset so that [y * pitch + x] is the halo cell of own (x, y)
+  float* down[5];
+};
+
 // ---- launchers (step_kernels.cu) ------------------------------------------------------
 // Fused K-level step over tile rows [ty0, ty1) of the strip; reads side `src`, writes 1-src.
 // Returns the number of tile rows for the strip through tiles_y when called with ty1 < 0.
@@ -86,8 +108,11 @@ cudaError_t stream_build_tma(const Geom& g, const Planes& p, int side, TmaSet* o
 cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c,
                           int lr0, int lr1, cudaStream_t st, int impl, uint32_t* sched, int cta_budget = 0);
 // Band kernel (band_kernels.cu): the streaming schedule in lock step; same row descriptors as the ring kernel.
+// edge != nullptr: a strip's whole block in one launch — rows [lr0, lr0 + e_top) and [lr1 - e_bot, lr1) are edge pieces
+// (taken first), the rows between them interior pieces.
 cudaError_t launch_band(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c,
-                        int lr0, int lr1, cudaStream_t st, uint32_t* sched, int cta_budget);
+                        int lr0, int lr1, cudaStream_t st, uint32_t* sched, int cta_budget, const BandEdge* edge = nullptr,
+                        int e_top = 0, int e_bot = 0);
 int stream_strip_width();
 cudaError_t launch_unfused_update(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st);
 cudaError_t launch_unfused_apply(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st);
