@@ -197,9 +197,10 @@ def run_reference(args):
 def workload_config(args, world):
     W = args.size
     Hg = args.size if args.strong else args.size * world
+    tiled = "" if (args.strong or world == 1) else f" — the {W}x{W} scene repeated {world}x along y, one copy per GPU"
     return {
         "workload": f"{W}x{Hg} reference-scene fBm terrain (value noise octaves 2..10, persistence 0.43, seed 231656522) + central lake, "
-                    f"open (reference) boundary, no sources; BASELINE config {'4/5 (strong)' if args.strong else '3 per GPU'}",
+                    f"open (reference) boundary, no sources; BASELINE config {'4/5 (strong)' if args.strong else '3 per GPU'}{tiled}",
         "grid": [W, Hg], "backend": args.backend, "temporal_block": args.tb if args.backend in ("tb", "stream", "band") else 1,
         "decomposition": f"{world} row strip(s), halo rows pushed over NVLink by the step kernels' stream (no collective)",
         "kernel_blocking": "column strips of 128 cells marched top to bottom, rows skewed in time (no halo rows recomputed), k steps per HBM round trip" if args.backend in ("band", "stream") else "overlapped tiles",
@@ -238,7 +239,10 @@ def run_b200(args):
     k = args.tb if args.backend in ("tb", "stream", "band") else 1
     sim = tws.Terrain(W, height=Hg, rows=plan.rows(rank), backend=backend, temporal_block=k, device=local)
     tws.connect_strips(sim, plan, rank)
-    sim.CreateHeightmapFromNoiseAndResetSim()
+    # weak scaling: every GPU's strip is the SAME W x W scene (the generator's terrain is periodic, so the tiles join
+    # seamlessly) — per-GPU work is then fixed as N grows, which a scene stretched over W x (W*N) is not
+    tile = 0 if args.strong else W
+    sim.CreateHeightmapFromNoiseAndResetSim(tileHeight=tile)
     sim.sync()
     cells_global = W * Hg
     cells_local = W * sim.rows
@@ -351,7 +355,7 @@ def run_b200(args):
     if args.verify_strips and world > 1:
         n_chk = 12
         barrier()                                    # strips must be quiescent around a reset
-        sim.CreateHeightmapFromNoiseAndResetSim()
+        sim.CreateHeightmapFromNoiseAndResetSim(tileHeight=tile)
         barrier()
         sim.inject_brush(W / 2 + 0.25, plan.rows(1)[0] - 0.5, 5.0, 64.0)
         sim.step(n_chk)
@@ -361,7 +365,7 @@ def run_b200(args):
         dist.gather_object(mine, parts, dst=0)
         if rank == 0:
             with tws.Terrain(W, height=Hg, backend=tws.BACKEND_UNFUSED, device=local) as whole:
-                whole.CreateHeightmapFromNoiseAndResetSim()
+                whole.CreateHeightmapFromNoiseAndResetSim(tileHeight=tile)
                 whole.inject_brush(W / 2 + 0.25, plan.rows(1)[0] - 0.5, 5.0, 64.0)
                 whole.step(n_chk)
                 ok = (np.array_equal(np.concatenate([p[0] for p in parts]).view(np.uint32), whole.readback(tws.FIELD_WATER).view(np.uint32))

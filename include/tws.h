@@ -148,6 +148,12 @@ tws_status tws_readback(tws_sim* s, tws_field field, void* host, size_t bytes);
  * GPU, bit-identical to the reference's CPU fill. */
 tws_status tws_reset_reference_scene(tws_sim* s, uint32_t seed, float height_scale,
                                      int32_t octave_lo, int32_t octave_hi, float persistence);
+/* EXTENSION: the same generator evaluated for a width x tile_height grid and repeated every
+ * tile_height rows (0 = height: the reference scene).  Weak-scaling workloads use it so that
+ * every strip of tile_height rows holds the identical scene. */
+tws_status tws_reset_reference_scene_tiled(tws_sim* s, uint32_t seed, float height_scale,
+                                           int32_t low_octave, int32_t high_octave, float persistence,
+                                           int32_t tile_height);
 
 /* Replaces Terrain::ApplyRadialWaterBrush (Terrain.cpp:150-168) + waterBrush.comp:
  * tws_inject_brush_world takes the world XZ position like the reference and derives the

@@ -90,6 +90,7 @@ SYMBOLS = {
     "tws_upload": (C.c_int, [_SIM, C.c_int, C.c_void_p, C.c_size_t]),
     "tws_readback": (C.c_int, [_SIM, C.c_int, C.c_void_p, C.c_size_t]),
     "tws_reset_reference_scene": (C.c_int, [_SIM, C.c_uint32, C.c_float, C.c_int32, C.c_int32, C.c_float]),
+    "tws_reset_reference_scene_tiled": (C.c_int, [_SIM, C.c_uint32, C.c_float, C.c_int32, C.c_int32, C.c_float, C.c_int32]),
     "tws_inject_brush": (C.c_int, [_SIM, C.c_float, C.c_float, C.c_float, C.c_float]),
     "tws_inject_brush_world": (C.c_int, [_SIM, C.c_float, C.c_float, C.c_float]),
     "tws_step": (C.c_int, [_SIM, C.c_int32]),

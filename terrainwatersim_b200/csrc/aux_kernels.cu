@@ -68,15 +68,17 @@ __device__ float noise3d(const float* white, float cx, float cy, float cz, int p
 }
 
 __global__ void __launch_bounds__(256) scene_kernel(Geom g, float* h, float* d /* local row 0 */, const float* __restrict__ white_g,
-                                                    float height_scale, int lo, int hi, float persistence, int lr0, int lr1) {
+                                                    float height_scale, int lo, int hi, float persistence, int lr0, int lr1, int tile_h) {
   __shared__ float white[4096];
   for (int i = threadIdx.x; i < 4096; i += blockDim.x) white[i] = white_g[i];
   __syncthreads();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= g.W) return;
-  const float mx = __fdiv_rn(1.0f, (float)(g.W - 1)), my = __fdiv_rn(1.0f, (float)(g.Hg - 1));
+  // tile_h < Hg: the scene of a W x tile_h grid repeated down the grid (weak-scaling workloads: every strip of
+  // tile_h rows is the same scene); the reference case is tile_h == Hg
+  const float mx = __fdiv_rn(1.0f, (float)(g.W - 1)), my = __fdiv_rn(1.0f, (float)(tile_h - 1));
   for (int lr = lr0 + blockIdx.y; lr < lr1; lr += gridDim.y) {
-    const int gy = g.row0 + lr;
+    const int gy = ((g.row0 + lr) % tile_h + tile_h) % tile_h;
     const float cx = mx * (float)x, cy = my * (float)gy, cz = 0.0f;
     float res = 0.0f, amplitude = 1.0f, frequency = (float)(1 << lo);
     for (int i = lo; i <= hi; ++i) {
@@ -97,11 +99,11 @@ __global__ void __launch_bounds__(256) scene_kernel(Geom g, float* h, float* d /
 }
 
 cudaError_t launch_scene(const Geom& g, const Planes& p, int side, const float* white_dev, float height_scale, int lo, int hi,
-                         float persistence, cudaStream_t st) {
+                         float persistence, int tile_h, cudaStream_t st) {
   const size_t off = (size_t)TWS_HALO_ROWS * g.pitch;
   const int lr0 = g.has_up ? -TWS_HALO_ROWS : 0, lr1 = g.rows + (g.has_down ? TWS_HALO_ROWS : 0);
   dim3 block(256), grid((g.W + 255) / 256, (lr1 - lr0) < 4096 ? (lr1 - lr0) : 4096);
-  scene_kernel<<<grid, block, 0, st>>>(g, p.h + off, p.d[side] + off, white_dev, height_scale, lo, hi, persistence, lr0, lr1);
+  scene_kernel<<<grid, block, 0, st>>>(g, p.h + off, p.d[side] + off, white_dev, height_scale, lo, hi, persistence, lr0, lr1, tile_h);
   return cudaGetLastError();
 }
 

@@ -652,7 +652,14 @@ static void white_noise_table(uint32_t seed, float* out) {
 }
 
 tws_status tws_reset_reference_scene(tws_sim* s, uint32_t seed, float height_scale, int32_t lo, int32_t hi, float persistence) {
+  return tws_reset_reference_scene_tiled(s, seed, height_scale, lo, hi, persistence, 0);
+}
+
+tws_status tws_reset_reference_scene_tiled(tws_sim* s, uint32_t seed, float height_scale, int32_t lo, int32_t hi, float persistence,
+                                           int32_t tile_height) {
   if (!s) return TWS_ERR_INVALID;
+  if (tile_height != 0 && (tile_height < 2 || tile_height > s->geom.Hg)) return fail(s, TWS_ERR_INVALID, "tile_height must be 0 or in [2, height]");
+  const int tile_h = tile_height ? tile_height : s->geom.Hg;
   if (lo < 0 || hi < lo || hi > 24) return fail(s, TWS_ERR_INVALID, "octave range must satisfy 0 <= lo <= hi <= 24");
   if (bad_float(height_scale) || bad_float(persistence)) return fail(s, TWS_ERR_INVALID, "height_scale/persistence must be finite");
   if (s->geom.W < 2 || s->geom.Hg < 2) return fail(s, TWS_ERR_INVALID, "reference scene needs a grid of at least 2x2");
@@ -666,7 +673,7 @@ tws_status tws_reset_reference_scene(tws_sim* s, uint32_t seed, float height_sca
   // flux = 0 (Terrain.cpp:230-234), both sides, halos included; depth/terrain regenerated.
   for (int side = 0; side < 2; ++side)
     for (int i = 0; i < 4; ++i) TWS_CUDA(s, cudaMemsetAsync(s->planes.F[side][i], 0, s->plane_elems * sizeof(float), s->st_main));
-  TWS_CUDA(s, launch_scene(s->geom, s->planes, s->cur, s->white_dev, height_scale, lo, hi, persistence, s->st_main));
+  TWS_CUDA(s, launch_scene(s->geom, s->planes, s->cur, s->white_dev, height_scale, lo, hi, persistence, tile_h, s->st_main));
   s->launches += 1;
   s->accumulator = 0.0;
   TWS_CUDA(s, cudaStreamSynchronize(s->st_main));

@@ -120,7 +120,7 @@ cudaError_t launch_unfused_apply(const Geom& g, const Planes& p, int side, const
 // ---- launchers (aux_kernels.cu) -------------------------------------------------------
 cudaError_t launch_brush(const Geom& g, float* d, float cx, float cy, float intensity, float size_sq, cudaStream_t st, int* launched);
 cudaError_t launch_scene(const Geom& g, const Planes& p, int side, const float* white_dev, float height_scale, int lo, int hi,
-                         float persistence, cudaStream_t st);
+                         float persistence, int tile_h, cudaStream_t st);
 cudaError_t launch_pack_flux(const Geom& g, const Planes& p, int side, float* aos, int lr0, int nrows, bool to_aos, cudaStream_t st);
 cudaError_t launch_pack_info(const Geom& g, const Planes& p, int side, float* aos, int lr0, int nrows, bool to_aos, cudaStream_t st);
 // one level of the RGBA32F mip chain (2x2 box, see aux_kernels.cu): dst (dw x dh texels) <- src (sw x sh texels)

@@ -106,9 +106,11 @@ class Terrain:
         self._check(self._lib.tws_set_flow_acceleration(self._sim, float(v)))
 
     def CreateHeightmapFromNoiseAndResetSim(self, seed: int = REFERENCE_SEED, heightScale: float = REFERENCE_HEIGHT_SCALE,
-                                            lowOctave: int = 2, highOctave: int = 10, persistence: float = 0.43) -> None:
-        """Terrain.cpp:200-238 preceded by Random::Init(seed) (Application.cpp:57)."""
-        self._check(self._lib.tws_reset_reference_scene(self._sim, seed, heightScale, lowOctave, highOctave, persistence))
+                                            lowOctave: int = 2, highOctave: int = 10, persistence: float = 0.43,
+                                            tileHeight: int = 0) -> None:
+        """Terrain.cpp:200-238 preceded by Random::Init(seed) (Application.cpp:57).  tileHeight (extension): the scene
+        of a width x tileHeight grid repeated every tileHeight rows (0: the reference scene over the whole grid)."""
+        self._check(self._lib.tws_reset_reference_scene_tiled(self._sim, seed, heightScale, lowOctave, highOctave, persistence, int(tileHeight)))
 
     # ---- helpers ------------------------------------------------------------------------------
     def step(self, n: int = 1) -> None:

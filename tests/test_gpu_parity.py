@@ -186,6 +186,21 @@ def test_gpu_scene_generator_matches_oracle(tws, oracle_omp, W, H):
         assert np.array_equal(bits(sim.readback(tws.FIELD_TERRAIN_INFO)), bits(s2))
 
 
+@pytest.mark.parametrize("W,H,tile", [(300, 600, 200), (256, 512, 256), (64, 100, 37)])
+def test_gpu_tiled_scene_is_the_small_scene_repeated(tws, oracle_omp, W, H, tile):
+    """Extension used by the weak-scaling bench: tws_reset_reference_scene_tiled = the W x tile scene of the
+    reference generator repeated every `tile` rows (the last copy cut off), bit for bit."""
+    one = oracle_omp.create_scene(W, tile)
+    want = np.concatenate([one] * ((H + tile - 1) // tile))[:H]
+    with make_sim(tws, W, H, 5, 2) as sim:
+        sim.CreateHeightmapFromNoiseAndResetSim(tileHeight=tile)
+        got = sim.readback(tws.FIELD_TERRAIN_INFO)
+        assert np.array_equal(bits(got), bits(want))
+        assert np.array_equal(sim.readback(tws.FIELD_FLUX), np.zeros((H, W, 4), np.float32))
+        with pytest.raises(tws.TwsError):
+            sim.CreateHeightmapFromNoiseAndResetSim(tileHeight=H + 1)
+
+
 def test_gpu_scene_generator_8192_golden(tws, oracle_omp):
     with make_sim(tws, 8192, 8192, tws.BACKEND_FUSED, 1) as sim:
         sim.CreateHeightmapFromNoiseAndResetSim()
