@@ -213,10 +213,12 @@ tws_status tws_device_view(tws_sim* s, tws_field field, void** device_ptr, int64
  * handle; the owner passes the handles of the strip above (rows < row_begin) and below
  * (rows >= row_end) to tws_halo_connect (NULL = global edge).  Sims in one process use
  * cudaDeviceEnablePeerAccess, sims in different processes CUDA IPC.  During tws_step
- * each strip pushes its freshly computed edge rows into the neighbours' halo rows and
- * raises a step flag in the neighbour's memory; the neighbour's edge kernels wait on
- * that flag while its interior kernels run.  tws_halo_refresh pushes the current state
- * (after upload / reset / inject); call it on all strips, then tws_sync + a host barrier. */
+ * each strip stores its freshly computed edge rows also into the neighbours' halo rows
+ * (peer stores over NVLink from inside the step kernel) and raises a step flag in the
+ * neighbour's memory; the neighbour's edge rows wait on that flag while its interior
+ * rows are computed.  tws_halo_refresh pushes the current state (after upload / reset /
+ * inject); call it on all strips, then tws_sync + a host barrier.  Strips that share
+ * one device are a test configuration: their launches wait for each other on the GPU. */
 tws_status tws_halo_export(tws_sim* s, tws_halo_handle* out);
 tws_status tws_halo_connect(tws_sim* s, const tws_halo_handle* up, const tws_halo_handle* down);
 tws_status tws_halo_refresh(tws_sim* s);

@@ -84,6 +84,52 @@ def test_strips_in_one_process_match_whole_grid(tws, oracle_omp, nstrips, k, bac
             s.close()
 
 
+@pytest.mark.parametrize("rows_per_strip,nstrips,k,backend", [(40, 3, 4, 5), (10, 4, 4, 5), (9, 3, 2, 5), (16, 3, 3, 5), (12, 3, 3, 4), (40, 3, 2, 3)])
+def test_strips_closed_boundary_with_sources(tws, oracle_omp, rows_per_strip, nstrips, k, backend):
+    """Extensions across strip seams: closed boundary (the wall rule applies at the GLOBAL edge only), rain and
+    evaporation, a wide grid (three column strips of the streaming kernels), and strips so short that a strip is
+    nothing but edge rows pushed to BOTH neighbours (the band kernel's exchange is fused into its step launch)."""
+    W, H, steps = 300, rows_per_strip * nstrips, 20
+    h, d = bumpy(W, H, seed=21)
+    c = oracle_omp.derive_consts(float(W), W)
+    dt = float(np.float32(1.0) / np.float32(60.0))
+    rain, evap = 0.8, 0.3
+    rs, es = float(np.float32(dt * np.float32(rain))), float(np.float32(dt * np.float32(evap)))
+    t, f, v = new_state(h, d)
+    oracle_omp.step(t, f, v, c, steps, boundary=1, rain_step=rs, evap_step=es)
+    bounds = [(i * rows_per_strip, (i + 1) * rows_per_strip) for i in range(nstrips)]
+    sims = [tws.Terrain(W, height=H, rows=bounds[i], backend=backend, temporal_block=k, device=i % n_gpus(),
+                        boundary=tws.BOUNDARY_CLOSED, rain_rate=rain, evaporation_rate=evap) for i in range(nstrips)]
+    try:
+        handles = [s.halo_export() for s in sims]
+        for i, s in enumerate(sims):
+            s.halo_connect(handles[i - 1] if i > 0 else None, handles[i + 1] if i + 1 < nstrips else None)
+        for i, s in enumerate(sims):
+            r0, r1 = bounds[i]
+            s.upload(tws.FIELD_TERRAIN, h[r0:r1]); s.upload(tws.FIELD_WATER, d[r0:r1])
+        for s in sims:
+            s.halo_refresh()
+        for s in sims:
+            s.sync()
+        done = 0
+        while done < steps:
+            n = min(k, steps - done)               # one block per call: one host thread feeds all strips
+            for s in sims:
+                s.step(n)
+            done += n
+        for s in sims:
+            s.sync()
+        gd = np.concatenate([s.readback(tws.FIELD_WATER) for s in sims])
+        gf = np.concatenate([s.readback(tws.FIELD_FLUX) for s in sims])
+        gv = np.concatenate([s.readback(tws.FIELD_VELOCITY) for s in sims])
+        assert np.array_equal(gd.view(np.uint32), t[..., 3].view(np.uint32))
+        assert np.array_equal(gf.view(np.uint32), f.view(np.uint32))
+        assert np.array_equal(gv.view(np.uint16), v.view(np.uint16))
+    finally:
+        for s in sims:
+            s.close()
+
+
 def test_strip_scene_generation_needs_no_exchange(tws, oracle_omp):
     W, H = 256, 256
     plan = tws.plan_strips(H, 2)
