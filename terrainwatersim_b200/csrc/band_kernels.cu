@@ -98,6 +98,32 @@ struct BandSched {
 #ifndef TWS_BAND_SPLIT
 #define TWS_BAND_SPLIT 1
 #endif
+// Suspend-time hint (ns) of the barrier waits: a waiting warp sleeps in hardware until its phase completes (or the
+// hint runs out) instead of coming back after the short default time limit and re-issuing the wait loop — waiting
+// warps share their scheduler with working ones, so every spin instruction is taken from a row that could make
+// progress.  0: no hint.
+#ifndef TWS_BAND_SUSPEND_NS
+#define TWS_BAND_SUSPEND_NS 0
+#endif
+#ifndef TWS_BAND_SUSPEND_FULL_NS
+#define TWS_BAND_SUSPEND_FULL_NS 0
+#endif
+// wait for a TMA landing buffer (same loop as mbar_wait, optionally with a suspend-time hint)
+__device__ __forceinline__ void band_wait_full(uint64_t* bar, uint32_t parity) {
+#if TWS_BAND_SUSPEND_FULL_NS
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)TWS_BAND_SUSPEND_FULL_NS) : "memory");
+  } while (!done);
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 struct GroupSync {
   uint32_t bar;        // shared address of the group's mbarrier
   uint32_t phase;      // parity of the phase the next wait() waits for
@@ -115,14 +141,18 @@ struct GroupSync {
         ".reg .u32 n;\n"
         "mov.u32 n, 0;\n"
         "TWS_GS_LOOP:\n"
+#if TWS_BAND_SUSPEND_NS
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#endif
         "@p bra TWS_GS_DONE;\n"
         "add.u32 n, n, 1;\n"
         "setp.gt.u32 q, n, 16777216;\n"
         "@q trap;\n"                                      // a barrier that never completes is a bug; a trap beats a hung GPU
         "bra TWS_GS_LOOP;\n"
         "TWS_GS_DONE:\n"
-        "}\n" ::"r"(bar), "r"(phase) : "memory");
+        "}\n" ::"r"(bar), "r"(phase), "r"((uint32_t)TWS_BAND_SUSPEND_NS) : "memory");
     phase ^= 1u;
   }
 };
@@ -591,7 +621,7 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
       // ---- half-pass 0: registers <- landing buffers; publish H; prefetch this warp's rows of the next band ----
       const bool loaded = i0 + warp < N;
       if (loaded) {
-        mbar_wait(full, parity);
+        band_wait_full(full, parity);
         parity ^= 1u;
 #pragma unroll
         for (int q = 0; q < R; ++q) {

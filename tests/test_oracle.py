@@ -263,3 +263,59 @@ def test_brush_center_and_footprint(oracle):
     dist = ((31.5 - xx) ** 2 + (20.0 - yy) ** 2) / 32.0
     assert np.array_equal(t[..., 3] != 1.0, dist < 1.0)
     assert t[20, 31, 3] == f32(1.0 + (1.0 - 0.25 / 32.0) * 2.0)
+
+
+# ---- a second, independent transcription -------------------------------------------------------------
+def _numpy_step(t, f, consts):
+    """flowUpdate.comp:26-62 then flowApply.comp:30-52 as whole-image numpy float32 expressions, written from the
+    shader text independently of oracle/tws_oracle.cpp (different structure: padded images instead of per-cell
+    neighbour loads).  Out-of-range imageLoad = 0 is the zero padding.  Returns the RG16F flow map."""
+    fr, ac, ai = (np.float32(x) for x in consts)
+    H, W = t.shape[:2]
+    hw = np.zeros((H + 2, W + 2), np.float32)
+    hw[1:-1, 1:-1] = t[..., 3] + t[..., 0]                     # terrainInfo.a + terrainInfo.r  (:34-40)
+    own = hw[1:-1, 1:-1]
+    new = np.empty((H, W, 4), np.float32)
+    new[..., 0] = own - hw[1:-1, 2:]                           # X1 = x+1  (:44)
+    new[..., 1] = own - hw[1:-1, :-2]                          # X0 = x-1  (:45)
+    new[..., 2] = own - hw[2:, 1:-1]                           # Y1 = y+1  (:46)
+    new[..., 3] = own - hw[:-2, 1:-1]                          # Y0 = y-1  (:47)
+    new = f * fr + new * ac                                    # :53 (each product and the sum rounded to binary32)
+    new = np.maximum(np.float32(0), new)                       # :54
+    total = (((new[..., 0] + new[..., 1]) + new[..., 2]) + new[..., 3]) * ai      # :57
+    a = t[..., 3]
+    over = total > a                                           # :58
+    with np.errstate(divide="ignore", invalid="ignore"):       # 0/0 where the branch is not taken
+        f[...] = np.where(over[..., None], new * (a / total)[..., None], new)     # :59, :62
+    fp = np.zeros((H + 2, W + 2, 4), np.float32)
+    fp[1:-1, 1:-1] = f
+    x1 = fp[1:-1, 2:, 1]; x0 = fp[1:-1, :-2, 0]; y1 = fp[2:, 1:-1, 3]; y0 = fp[:-2, 1:-1, 2]      # flowApply.comp:32-35
+    ingoing = ((x1 + x0) + y1) + y0                            # :38
+    outgoing = ((f[..., 0] + f[..., 1]) + f[..., 2]) + f[..., 3]                   # :39
+    t[..., 3] = np.maximum(np.float32(0), a + (ingoing - outgoing) * ai)           # :41
+    v = np.empty((H, W, 2), np.float32)
+    v[..., 0] = (x1 - f[..., 0]) - (x0 - f[..., 1])            # :45
+    v[..., 1] = (y1 - f[..., 2]) - (y0 - f[..., 3])            # :46
+    return v.astype(np.float16)                                # imageStore to rg16f: round to nearest even
+
+
+@pytest.mark.parametrize("W,H,seed", [(48, 40, 1), (33, 7, 2), (5, 61, 3)])
+def test_cxx_oracle_equals_an_independent_numpy_transcription(oracle, W, H, seed):
+    """Two transcriptions of the two shaders written separately (C++ per-cell loops, numpy whole-image
+    expressions) agree bit for bit over 40 steps of a rough random scene with dry, wet and draining cells —
+    a guard against transcription slips, since the reference offers no golden vector for the step."""
+    rng = np.random.default_rng(seed)
+    h = (rng.random((H, W)) * 8).astype(np.float32)
+    d = (rng.random((H, W)) * 4 * (rng.random((H, W)) > 0.4)).astype(np.float32)
+    c = oracle.derive_consts(float(max(W, H)), max(W, H))
+    t1, f1, v1 = new_state(h, d)
+    t2, f2, _ = new_state(h, d)
+    scaled = 0
+    for step in range(40):
+        oracle.step(t1, f1, v1, c, 1)
+        v2 = _numpy_step(t2, f2, c)
+        assert np.array_equal(t1.view(np.uint32), t2.view(np.uint32)), f"TerrainData differs at step {step}"
+        assert np.array_equal(f1.view(np.uint32), f2.view(np.uint32)), f"Flow differs at step {step}"
+        assert np.array_equal(v1.view(np.uint16), v2.view(np.uint16)), f"FlowMap differs at step {step}"
+        scaled += int(((t2[..., 3] == 0) & (f2.sum(axis=-1) > 0)).sum())
+    assert scaled > 0                      # the clamp branch (:58-59) was exercised
