@@ -14,7 +14,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libtws.so"
 SOURCES = ["tws_api.cu", "step_kernels.cu", "stream_kernels.cu", "band_kernels.cu", "aux_kernels.cu"]
-HEADERS = [CSRC / "tws_internal.h", CSRC / "cell_math.cuh", PKG_DIR.parent / "include" / "tws.h"]
+HEADERS = [CSRC / "tws_internal.h", CSRC / "cell_math.cuh", CSRC / "band_schedule.h", PKG_DIR.parent / "include" / "tws.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

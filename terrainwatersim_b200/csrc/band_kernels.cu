@@ -35,6 +35,7 @@
 // results are never stored (store guards) and by the schedule never reach a kept value, and computing
 // them keeps the half-pass free of per-row branches.
 #include "cell_math.cuh"
+#include "band_schedule.h"
 
 #include <algorithm>
 #include <climits>
@@ -66,23 +67,6 @@ struct BandRow {       // per-row context (the lane's column offset and store ma
   bool row_in;         // the row exists in the global grid
   bool store;          // the row is an output row of this piece
   size_t go;           // element offset of the lane's group in the output planes
-};
-
-// Work list of one launch.  A piece is (row segment, column strip); every warp group starts on piece
-// `its index` and then takes pieces from a device-wide counter, so groups whose cells need the slow
-// paths (the IEEE division of draining wet cells: lake and shore regions cost up to 1.4x the
-// instructions of dry land) simply take fewer pieces.  Segments shrink geometrically down the strip
-// ("guided" schedule: about half of the remaining rows per level), so the pieces handed out last are
-// small and the groups finish together, while most rows are covered by long pieces whose 2K warm-up /
-// feeder rows amortise.  Piece p = (segment p / nstrips, strip p % nstrips): the pieces in flight at any
-// time are the same rows of neighbouring strips, which keeps their shared halo columns in L2.
-struct BandSched {
-  static constexpr int MAXLEV = 14;
-  int nlev, npieces;
-  int seg0[MAXLEV];    // first segment of level l
-  int y0[MAXLEV];      // first row (relative to lr0) of level l
-  int yend[MAXLEV];    // end row of level l
-  int size[MAXLEV];    // rows per segment of level l (the last segment of a level may be shorter)
 };
 
 // Split-phase group barrier: one mbarrier per warp group, one arrival per warp.  arrive() right after a
@@ -532,14 +516,9 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
     // a group never holds more than a fraction of its fair share — which is also why a strip's tiny edge pieces come
     // LAST in the list (first, every group would fetch twice within microseconds and end up holding two long pieces).
     if (sched && warp == 0 && lane == 0) next_piece[grp][pp] = nvcta + (int)atomicAdd(sched, 1u);
-    const int seg = piece / nstrips, strip = piece - seg * nstrips;
-    int lev = 0;
-#pragma unroll 1
-    while (lev + 1 < sch.nlev && seg >= sch.seg0[lev + 1]) ++lev;
-    const int lev_end = sch.yend[lev];
-    const int ya_rel = sch.y0[lev] + (seg - sch.seg0[lev]) * sch.size[lev];
-    const int ya = lr0 + ya_rel;
-    const int yb = lr0 + (ya_rel + sch.size[lev] < lev_end ? ya_rel + sch.size[lev] : lev_end);
+    int lev, strip, ya_rel, yb_rel;
+    band_decode(sch, piece, nstrips, lev, strip, ya_rel, yb_rel);
+    const int ya = lr0 + ya_rel, yb = lr0 + yb_rel;
     const bool edge_piece = edge.nlev_edge != 0 && lev >= edge.lev_edge0;
     if (edge_piece) {
       // the halo rows this piece reads were stored by the neighbour's previous block: wait for its flag (it is
@@ -708,42 +687,6 @@ static int band_sm_count() {
   return cached[dev & 63] > 0 ? cached[dev & 63] : 148;
 }
 
-// Guided schedule (see BandSched): appends levels covering rows [y_begin, y_end) of `nstrips` strips for up to
-// `max_groups` warp groups to `s`; `seg` is the running segment count.
-static void band_schedule_rows(BandSched& s, int& seg, int y_begin, int y_end, int nstrips, int max_groups, int BR, int HP) {
-  const int rows = y_end - y_begin;
-  if (rows <= 0) return;
-  const long long total = (long long)rows * nstrips;
-  const int even = (int)((total + max_groups - 1) / max_groups);            // rows per group if the work were split evenly
-  // shortest segment: long enough that the 2K warm-up / feeder rows amortise (128 rows), but small grids are
-  // latency bound and rather use every SM (at least ~4 bands per piece)
-  const int smin = std::max(4 * BR, std::min(128, even));
-  // a piece computes rows + 2*HP rows in whole bands: sizes that make that a multiple of BR waste nothing
-  auto whole_bands = [&](int sz) { return std::max(BR, (sz + 2 * HP + BR - 1) / BR * BR) - 2 * HP; };
-  int size = whole_bands(std::max(smin, even / 2));
-  int y = y_begin;
-  while (y < y_end) {
-    const int l = s.nlev;
-    const int rem = y_end - y;
-    const bool rest = size <= whole_bands(smin) || l >= BandSched::MAXLEV - 3;      // two levels stay free for a strip's edge bands
-    const int n = rest ? (rem + size - 1) / size : std::max(1, rem / 2 / size);   // about half of what is left per level
-    const int cover = (int)std::min<long long>(rem, (long long)n * size);
-    s.seg0[l] = seg; s.y0[l] = y; s.yend[l] = y + cover; s.size[l] = size;
-    seg += n;
-    y += cover;
-    s.nlev = l + 1;
-    size = whole_bands(std::max(smin, size / 2));
-  }
-}
-// one level holding a single segment [y_begin, y_end): an edge band of a strip
-static void band_schedule_one(BandSched& s, int& seg, int y_begin, int y_end) {
-  if (y_end <= y_begin) return;
-  const int l = s.nlev;
-  s.seg0[l] = seg; s.y0[l] = y_begin; s.yend[l] = y_end; s.size[l] = y_end - y_begin;
-  seg += 1;
-  s.nlev = l + 1;
-}
-
 template <int K, bool EXT>
 static cudaError_t launch_band_k(const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
                                  cudaStream_t st, uint32_t* sched, int cta_budget, const BandEdge* edge, int e_top, int e_bot) {
@@ -771,25 +714,18 @@ static cudaError_t launch_band_k(const Geom& g, const Planes& p, const TmaSet& t
   // many CTAs, < 0: leave that many SMs free
   const int all_sms = band_sm_count();
   const int sms = cta_budget > 0 ? std::min(cta_budget, all_sms) : std::max(1, all_sms + cta_budget);
-  BandSched sch{};
   BandEdge ed{};
-  int seg = 0;
-  const int rel1 = lr1 - lr0;                            // schedule rows are relative to lr0
+  if (edge != nullptr) ed = *edge;
+  int lev_edge0 = 0, nlev_edge = 0, edge_segs = 0;
+  // a strip's block (edge != nullptr): the interior, then the edge bands — tiny pieces that fill the tail of the
+  // launch; the neighbours need them only for THEIR edge pieces at the end of their next block
+  const BandSched sch = band_build_schedule(lr1 - lr0, nstrips, sms * C::NGRP, C::BR, C::HP, edge != nullptr ? e_top : 0,
+                                            edge != nullptr ? e_bot : 0, &lev_edge0, &nlev_edge, &edge_segs);
   if (edge != nullptr) {
-    // a strip's block: the interior, then the edge bands — tiny pieces that fill the tail of the launch; the
-    // neighbours need them only for THEIR edge pieces at the end of their next block
-    ed = *edge;
-    band_schedule_rows(sch, seg, e_top, rel1 - e_bot, nstrips, sms * C::NGRP, C::BR, C::HP);
-    ed.lev_edge0 = sch.nlev;
-    const int seg_i = seg;
-    band_schedule_one(sch, seg, 0, e_top);
-    band_schedule_one(sch, seg, rel1 - e_bot, rel1);
-    ed.nlev_edge = sch.nlev - ed.lev_edge0;
-    ed.n_edge_warps = (unsigned)(seg - seg_i) * (unsigned)nstrips * (unsigned)C::NW;
-  } else {
-    band_schedule_rows(sch, seg, 0, rel1, nstrips, sms * C::NGRP, C::BR, C::HP);
+    ed.lev_edge0 = lev_edge0;
+    ed.nlev_edge = nlev_edge;
+    ed.n_edge_warps = (unsigned)edge_segs * (unsigned)nstrips * (unsigned)C::NW;
   }
-  sch.npieces = seg * nstrips;
   const int want = (sch.npieces + C::NGRP - 1) / C::NGRP;
   const int grid = want < 1 ? 1 : (want < sms ? want : sms);
   const int bias = g.has_up ? TWS_HALO_ROWS : 0;

@@ -113,3 +113,19 @@ def test_model_catches_a_single_buffered_slot():
     with pytest.raises(AssertionError):
         for seed in range(6):
             broken(12, 1, 4, 100, seed)
+
+
+def test_work_list_tiles_the_launch_exactly_once(tmp_path):
+    """The guided piece list (csrc/band_schedule.h, host code shared with the kernel launcher) and the decode the
+    kernel uses: every row of every strip in exactly one piece, interior sizes never growing, edge bands last,
+    no level overflow — over a sweep of grid sizes, strip counts, group counts, K and edge configurations."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "band_schedule_check"
+    cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    res = subprocess.run([cxx, "-std=c++17", "-O2", "-Wall", "-Werror", str(root / "tests" / "band_schedule_check.cpp"), "-o", str(exe)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith("OK "), out.stdout + out.stderr
