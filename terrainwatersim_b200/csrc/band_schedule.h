@@ -9,6 +9,14 @@
 #define TWS_HD
 #endif
 
+// tuning knobs of the guided schedule (defaults measured on 8192^2 / 32768^2, see profiles/)
+#ifndef TWS_BAND_SMIN
+#define TWS_BAND_SMIN 128        // shortest segment (rows) on large grids
+#endif
+#ifndef TWS_BAND_FIRST_DIV
+#define TWS_BAND_FIRST_DIV 2     // first-level segment = even share / this
+#endif
+
 namespace tws {
 
 // Work list of one launch.  A piece is (row segment, column strip); every warp group starts on piece
@@ -47,10 +55,10 @@ inline void band_schedule_rows(BandSched& s, int& seg, int y_begin, int y_end, i
   const int even = (int)((total + max_groups - 1) / max_groups);            // rows per group if the work were split evenly
   // shortest segment: long enough that the 2K warm-up / feeder rows amortise (128 rows), but small grids are
   // latency bound and rather use every SM (at least ~4 bands per piece)
-  const int smin = std::max(4 * BR, std::min(128, even));
+  const int smin = std::max(4 * BR, std::min(TWS_BAND_SMIN, even));
   // a piece computes rows + 2*HP rows in whole bands: sizes that make that a multiple of BR waste nothing
   auto whole_bands = [&](int sz) { return std::max(BR, (sz + 2 * HP + BR - 1) / BR * BR) - 2 * HP; };
-  int size = whole_bands(std::max(smin, even / 2));
+  int size = whole_bands(std::max(smin, even / TWS_BAND_FIRST_DIV));
   int y = y_begin;
   while (y < y_end) {
     const int l = s.nlev;

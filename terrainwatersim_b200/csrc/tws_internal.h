@@ -38,6 +38,8 @@ struct Control {
   alignas(128) uint32_t sched_edge[4];
 };
 
+static_assert(sizeof(Control) <= TWS_CTRL_BYTES, "the control block must fit in front of the planes");
+
 struct StepConsts {
   float friction, accel, area_inv;   // simulationCommon.glsl:1-13
   float rain_step, evap_step;        // EXT, already multiplied by dt
