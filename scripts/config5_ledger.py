@@ -21,7 +21,8 @@ ap.add_argument("--size", type=int, default=65536)
 ap.add_argument("--steps", type=int, default=1000)
 ap.add_argument("--rain", type=float, default=0.6)
 ap.add_argument("--evap", type=float, default=0.3)
-ap.add_argument("--fast-steps", type=int, default=0, help="extra steps with k=2 and no per-step ledger (long horizon, invariants only)")
+ap.add_argument("--fast-steps", type=int, default=0, help="extra steps with temporal blocking and no per-step ledger (long horizon, invariants only)")
+ap.add_argument("--backend", default="band", choices=["band", "tile"], help="band: band kernel (k=1 ledger, k=4 long run); tile: tile kernel (k=1 / k=2)")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -46,7 +47,8 @@ def barrier():
 
 
 res = {}
-with tws.Terrain(W, rows=plan.rows(rank), backend=tws.BACKEND_FUSED, device=local, rain_rate=a.rain, evaporation_rate=a.evap) as sim:
+B1, BK, KK = (tws.BACKEND_BAND_TB, tws.BACKEND_BAND_TB, 4) if a.backend == "band" else (tws.BACKEND_FUSED, tws.BACKEND_FUSED_TB, 2)
+with tws.Terrain(W, rows=plan.rows(rank), backend=B1, temporal_block=1, device=local, rain_rate=a.rain, evaporation_rate=a.evap) as sim:
     tws.connect_strips(sim, plan, rank)
     sim.CreateHeightmapFromNoiseAndResetSim()
     barrier()
@@ -64,11 +66,11 @@ with tws.Terrain(W, rows=plan.rows(rank), backend=tws.BACKEND_FUSED, device=loca
     out = allsum(out)
     V1 = allsum(sim.total_volume())
     expect = V0 + float(W) * W * a.steps * float(rs - es) - out
-    res = {"grid": [W, W], "gpus": world, "steps": a.steps, "V0": V0, "V1": V1, "boundary_outflow": out,
+    res = {"grid": [W, W], "gpus": world, "backend": a.backend, "long_run_temporal_block": KK, "steps": a.steps, "V0": V0, "V1": V1, "boundary_outflow": out,
            "net_source": float(W) * W * a.steps * float(rs - es), "closure_rel": (V1 - expect) / V1,
            "ledger_wall_s": wall, "ledger_Gcell_per_s": float(W) * W * a.steps / wall / 1e9}
 if a.fast_steps:
-    with tws.Terrain(W, rows=plan.rows(rank), backend=tws.BACKEND_FUSED_TB, temporal_block=2, device=local, rain_rate=a.rain,
+    with tws.Terrain(W, rows=plan.rows(rank), backend=BK, temporal_block=KK, device=local, rain_rate=a.rain,
                      evaporation_rate=a.evap) as sim:
         tws.connect_strips(sim, plan, rank)
         sim.CreateHeightmapFromNoiseAndResetSim()
