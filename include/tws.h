@@ -45,6 +45,10 @@ typedef enum tws_status {
 
 /* Which kernels run a step.  All of them produce bit-identical state. */
 typedef enum tws_backend {
+  TWS_BACKEND_AUTO = 0,     /* default: chosen at tws_create from the (strip's) cell count — the
+                               band kernel with 4 steps per launch from ~12 M cells up, the
+                               tile kernel with 2 below (measured crossover ~3072^2 on B200);
+                               `temporal_block` is ignored; see tws_backend_in_use          */
   TWS_BACKEND_UNFUSED = 1,  /* two kernels per step, mirroring the two dispatches of
                                Terrain.cpp:255-264 (in-place, no shared memory)          */
   TWS_BACKEND_FUSED = 2,    /* one TMA-staged shared-memory stencil kernel per step      */
@@ -54,7 +58,8 @@ typedef enum tws_backend {
                                per grid row, rows skewed in time instead of recomputed,
                                `temporal_block` steps per HBM round trip                  */
   TWS_BACKEND_BAND_TB = 5   /* the same skewed row streaming run in lock step: bands of rows,
-                               one __syncthreads per half-pass instead of per-row barriers */
+                               one group barrier per half-pass instead of per-row barriers,
+                               dynamic piece schedule, strip exchange fused into the launch */
 } tws_backend;
 
 typedef enum tws_boundary {
@@ -204,6 +209,8 @@ uint64_t   tws_kernel_launches(const tws_sim* s);
  * Terrain.cpp:253-265, up to 10 steps per frame).  Returns how many batches ran as a graph replay.
  * Environment TWS_GRAPHS=0 disables capture (every kernel launched individually). */
 uint64_t   tws_graph_replays(const tws_sim* s);
+/* The backend and steps-per-launch this sim runs with (what TWS_BACKEND_AUTO resolved to). */
+tws_status tws_backend_in_use(const tws_sim* s, int32_t* backend, int32_t* temporal_block);
 /* Raw device pointer and row pitch (in elements) of a planar field for zero-copy
  * consumers (CUDA interop); planes: TERRAIN, WATER (current), VELOCITY. */
 tws_status tws_device_view(tws_sim* s, tws_field field, void** device_ptr, int64_t* pitch_elems);

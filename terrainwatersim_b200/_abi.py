@@ -17,6 +17,7 @@ TWS_ERR_NOMEM = -3
 TWS_ERR_STATE = -4
 TWS_ERR_UNSUPPORTED = -5
 
+BACKEND_AUTO = 0
 BACKEND_UNFUSED = 1
 BACKEND_FUSED = 2
 BACKEND_FUSED_TB = 3
@@ -102,6 +103,7 @@ SYMBOLS = {
     "tws_elapsed_ms": (C.c_int, [_SIM, C.POINTER(C.c_float)]),
     "tws_kernel_launches": (C.c_uint64, [_SIM]),
     "tws_graph_replays": (C.c_uint64, [_SIM]),
+    "tws_backend_in_use": (C.c_int, [_SIM, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "tws_device_view": (C.c_int, [_SIM, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "tws_halo_export": (C.c_int, [_SIM, C.POINTER(TwsHaloHandle)]),
     "tws_halo_connect": (C.c_int, [_SIM, C.POINTER(TwsHaloHandle), C.POINTER(TwsHaloHandle)]),

@@ -453,7 +453,7 @@ void tws_default_params(tws_params* p) {
   p->world_size = 1024.0f;                                                      // Terrain.cpp:22
   p->steps_per_second = 60.0f; p->flow_damping = 0.98f; p->flow_acceleration = 10.0f;   // Terrain.cpp:28-30
   p->boundary = TWS_BOUNDARY_REFERENCE_OPEN;
-  p->backend = TWS_BACKEND_FUSED;
+  p->backend = TWS_BACKEND_AUTO;
   p->temporal_block = 1;
   p->device = 0;
 }
@@ -478,7 +478,7 @@ tws_status tws_create(const tws_params* p, tws_sim** out) {
   if (bad_float(p->flow_acceleration) || p->flow_acceleration < 0.0f) return fail(nullptr, TWS_ERR_INVALID, "tws_create: flow_acceleration must be >= 0");
   if (bad_float(p->rain_rate) || bad_float(p->evaporation_rate) || p->rain_rate < 0.0f || p->evaporation_rate < 0.0f)
     return fail(nullptr, TWS_ERR_INVALID, "tws_create: rain/evaporation must be >= 0");
-  if (p->backend < TWS_BACKEND_UNFUSED || p->backend > TWS_BACKEND_BAND_TB) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown backend");
+  if (p->backend < TWS_BACKEND_AUTO || p->backend > TWS_BACKEND_BAND_TB) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown backend");
   if (p->boundary != TWS_BOUNDARY_REFERENCE_OPEN && p->boundary != TWS_BOUNDARY_CLOSED) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown boundary");
   if ((p->backend == TWS_BACKEND_FUSED_TB || is_stream_backend(p->backend)) && (p->temporal_block < 1 || p->temporal_block > TWS_MAX_TB))
     return fail(nullptr, TWS_ERR_INVALID, "tws_create: temporal_block must be 1..4");
@@ -495,6 +495,16 @@ tws_status tws_create(const tws_params* p, tws_sim** out) {
   tws_sim* s = new (std::nothrow) tws_sim;
   if (!s) return fail(nullptr, TWS_ERR_NOMEM, "tws_create: out of host memory");
   s->prm = *p;
+  if (p->backend == TWS_BACKEND_AUTO) {
+    // Measured on B200 (scripts/crossover_perf.py, profiles/r01_crossover_tile_vs_band.log): small grids are latency
+    // bound and the tile kernel keeps more of the SM busy (209 vs 206 Gcell/s at 3072^2, 177 vs 165 at 2048^2); from
+    // 4096^2 up the band kernel wins (255 vs 218, 313 vs 235 at 8192^2).  Strips count their own cells.
+    const long long cells = (long long)p->width * (p->row_end - p->row_begin);
+    const bool big = cells >= 12LL * 1000 * 1000;
+    s->prm.backend = big ? TWS_BACKEND_BAND_TB : TWS_BACKEND_FUSED_TB;
+    s->prm.temporal_block = big ? 4 : 2;
+    p = &s->prm;
+  }
   s->K = (p->backend == TWS_BACKEND_FUSED_TB || is_stream_backend(p->backend)) ? p->temporal_block : 1;
   if (const char* gv = getenv("TWS_GRAPHS")) s->use_graphs = gv[0] != '0';
   DeviceGuard guard(p->device);
@@ -859,6 +869,13 @@ tws_status tws_elapsed_ms(tws_sim* s, float* ms) {
 }
 
 uint64_t tws_kernel_launches(const tws_sim* s) { return s ? s->launches : 0; }
+tws_status tws_backend_in_use(const tws_sim* s, int32_t* backend, int32_t* temporal_block) {
+  if (!s) return TWS_ERR_INVALID;
+  if (backend) *backend = s->prm.backend;
+  if (temporal_block) *temporal_block = s->K;
+  return TWS_OK;
+}
+
 uint64_t tws_graph_replays(const tws_sim* s) { return s ? s->graph_replays : 0; }
 
 tws_status tws_device_view(tws_sim* s, tws_field field, void** ptr, int64_t* pitch) {

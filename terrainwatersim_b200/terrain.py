@@ -31,7 +31,7 @@ class Terrain:
     """One simulation grid (or one row strip of it) resident on a B200."""
 
     def __init__(self, gridResolution: int = 1024, gridWorldSize: Optional[float] = None, *, height: Optional[int] = None,
-                 rows: Optional[Tuple[int, int]] = None, backend: int = _abi.BACKEND_FUSED, temporal_block: int = 1,
+                 rows: Optional[Tuple[int, int]] = None, backend: int = _abi.BACKEND_AUTO, temporal_block: int = 1,
                  boundary: int = _abi.BOUNDARY_REFERENCE_OPEN, device: int = 0, simulationStepsPerSecond: float = 60.0,
                  flowDamping: float = 0.98, flowAcceleration: float = 10.0, rain_rate: float = 0.0,
                  evaporation_rate: float = 0.0):
@@ -149,6 +149,12 @@ class Terrain:
 
     def kernel_launches(self) -> int:
         return int(self._lib.tws_kernel_launches(self._sim))
+
+    def backend_in_use(self) -> Tuple[int, int]:
+        """(backend, steps per launch) — what BACKEND_AUTO resolved to."""
+        b, k = C.c_int32(0), C.c_int32(0)
+        self._check(self._lib.tws_backend_in_use(self._sim, C.byref(b), C.byref(k)))
+        return int(b.value), int(k.value)
 
     def graph_replays(self) -> int:
         return int(self._lib.tws_graph_replays(self._sim))

@@ -422,3 +422,22 @@ def test_gl_interop_without_a_gl_context_fails_cleanly(tws):
         sim.gl_unregister(); sim.gl_unregister()
         sim.step(2)                                           # the sim is still usable
         assert np.isfinite(sim.total_volume())
+
+
+def test_auto_backend_resolves_by_grid_size_and_matches_the_oracle(tws, oracle):
+    """TWS_BACKEND_AUTO (the default of tws_default_params): tile kernel, 2 steps per launch, below ~12 M cells;
+    band kernel, 4 steps per launch, above (measured crossover, profiles/r01_crossover_tile_vs_band.log)."""
+    with tws.Terrain(1024) as sim:
+        assert sim.backend_in_use() == (tws.BACKEND_FUSED_TB, 2)
+    with tws.Terrain(4096) as sim:
+        assert sim.backend_in_use() == (tws.BACKEND_BAND_TB, 4)
+    with tws.Terrain(4096, rows=(1024, 2048)) as sim:            # a strip counts its own cells
+        assert sim.backend_in_use() == (tws.BACKEND_FUSED_TB, 2)
+    W, H = 250, 190
+    h, d = bumpy(W, H, seed=3)
+    t, f, v = new_state(h, d)
+    oracle.step(t, f, v, oracle.derive_consts(float(W), W), 13)
+    with tws.Terrain(W, height=H) as sim:
+        sim.upload(tws.FIELD_TERRAIN, h); sim.upload(tws.FIELD_WATER, d)
+        sim.step(13)
+        assert_state_equal(sim, tws, t, f, v, "auto")
