@@ -202,7 +202,7 @@ def workload_config(args, world):
         "workload": f"{W}x{Hg} reference-scene fBm terrain (value noise octaves 2..10, persistence 0.43, seed 231656522) + central lake, "
                     f"open (reference) boundary, no sources; BASELINE config {'4/5 (strong)' if args.strong else '3 per GPU'}{tiled}",
         "grid": [W, Hg], "backend": args.backend, "temporal_block": args.tb if args.backend in ("tb", "stream", "band") else 1,
-        "decomposition": f"{world} row strip(s), halo rows pushed over NVLink by the step kernels' stream (no collective)",
+        "decomposition": f"{world} row strip(s); edge rows are stored into the neighbours' halo rows by the step kernel itself (peer stores over NVLink, flag handshake, no collective)",
         "kernel_blocking": "column strips of 128 cells marched top to bottom, rows skewed in time (no halo rows recomputed), k steps per HBM round trip" if args.backend in ("band", "stream") else "overlapped tiles",
         "l2": "state >= 3.2 GB per GPU, far larger than the 126 MB L2 (inputs larger than L2, no flush needed)",
     }
