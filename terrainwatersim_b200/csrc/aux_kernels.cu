@@ -167,6 +167,40 @@ __global__ void __launch_bounds__(256) mip_level_kernel(const float4* __restrict
     dst[(long long)y * dw + x] = o;
   }
 }
+// The tail of the chain — every level from `first` on, once a level has shrunk to a few thousand texels — in ONE
+// launch of one CTA: at the reference's own size (1024^2, 11 levels) the small levels are pure launch latency, and
+// the renderer hand-off runs every frame.  Same arithmetic as mip_level_kernel; the levels are produced in order,
+// a block barrier between them (plain loads: a level is read by the CTA that has just written it).
+__global__ void __launch_bounds__(1024) mip_tail_kernel(float4* base, int W, int H, int first, int last) {
+  long long off = 0;                                   // offset (texels) and size of level `first - 1`
+  int w = W, h = H;
+  for (int l = 0; l < first - 1; ++l) { off += (long long)w * h; w = max(1, w >> 1); h = max(1, h >> 1); }
+  for (int l = first; l < last; ++l) {
+    const int sw = w, sh = h;
+    const float4* src = base + off;
+    off += (long long)sw * sh;
+    w = max(1, sw >> 1); h = max(1, sh >> 1);
+    float4* dst = base + off;
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+      const int x = i % w, y = i / w;
+      const int x0 = min(2 * x, sw - 1), x1 = min(2 * x + 1, sw - 1);
+      const int r0 = min(2 * y, sh - 1) * sw, r1 = min(2 * y + 1, sh - 1) * sw;
+      const float4 a = src[r0 + x0], b = src[r0 + x1], c = src[r1 + x0], d = src[r1 + x1];
+      float4 o;
+      o.x = __fmul_rn(__fadd_rn(__fadd_rn(a.x, b.x), __fadd_rn(c.x, d.x)), 0.25f);
+      o.y = __fmul_rn(__fadd_rn(__fadd_rn(a.y, b.y), __fadd_rn(c.y, d.y)), 0.25f);
+      o.z = __fmul_rn(__fadd_rn(__fadd_rn(a.z, b.z), __fadd_rn(c.z, d.z)), 0.25f);
+      o.w = __fmul_rn(__fadd_rn(__fadd_rn(a.w, b.w), __fadd_rn(c.w, d.w)), 0.25f);
+      dst[i] = o;
+    }
+    __syncthreads();
+  }
+}
+cudaError_t launch_mip_tail(float* base, int W, int H, int first, int last, cudaStream_t st) {
+  if (first >= last) return cudaSuccess;
+  mip_tail_kernel<<<1, 1024, 0, st>>>((float4*)base, W, H, first, last);
+  return cudaGetLastError();
+}
 cudaError_t launch_mip_level(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t st) {
   dim3 block(256), grid((dw + 255) / 256, dh < 2048 ? dh : 2048);
   mip_level_kernel<<<grid, block, 0, st>>>((const float4*)src, sw, sh, (float4*)dst, dw, dh);

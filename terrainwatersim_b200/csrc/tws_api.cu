@@ -1019,11 +1019,18 @@ tws_status publish_chain(tws_sim* s) {
   if (r) return r;
   const int L = tws_mip_levels(g.W, g.rows);
   float* base = (float*)s->packed_info;
+  // large levels: one launch each; from the first level of <= 16 K texels on, the whole tail in one launch
+  int first_tail = L;
   for (int l = 1; l < L; ++l) {
     int32_t sw, sh, dw, dh; int64_t so, d_o;
     tws_mip_level_info(g.W, g.rows, l - 1, &sw, &sh, &so);
     tws_mip_level_info(g.W, g.rows, l, &dw, &dh, &d_o);
+    if ((long long)dw * dh <= 16384) { first_tail = l; break; }
     TWS_CUDA(s, launch_mip_level(base + so * 4, sw, sh, base + d_o * 4, dw, dh, s->st_main));
+    s->launches += 1;
+  }
+  if (first_tail < L) {
+    TWS_CUDA(s, launch_mip_tail(base, g.W, g.rows, first_tail, L, s->st_main));
     s->launches += 1;
   }
   s->published_levels = L;

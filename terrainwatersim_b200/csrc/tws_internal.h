@@ -127,6 +127,8 @@ cudaError_t launch_pack_flux(const Geom& g, const Planes& p, int side, float* ao
 cudaError_t launch_pack_info(const Geom& g, const Planes& p, int side, float* aos, int lr0, int nrows, bool to_aos, cudaStream_t st);
 // one level of the RGBA32F mip chain (2x2 box, see aux_kernels.cu): dst (dw x dh texels) <- src (sw x sh texels)
 cudaError_t launch_mip_level(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t st);
+// levels [first, last) of the chain at `base` (level L follows level L-1) in one single-CTA launch: the small tail
+cudaError_t launch_mip_tail(float* base, int W, int H, int first, int last, cudaStream_t st);
 cudaError_t launch_boundary_outflow(const Geom& g, const Planes& p, int side, double* out, cudaStream_t st);
 cudaError_t launch_volume(const Geom& g, const float* d, double* partials, int nblocks, cudaStream_t st);
 // copy `nrows` plane rows of `nplanes` planes: dst[i] + dst_row*pitch <- src[i] + src_row*pitch
