@@ -139,17 +139,17 @@ def dist_env():
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores (the ONLY place bench.py uses oracle/)
 # --------------------------------------------------------------------------------------------------
-def cpu_oracle_throughput(size: int, steps: int, warmup: int, budget_s: float):
+def cpu_oracle_throughput(size: int, steps: int, warmup: int, budget_s: float, openmp: bool = True):
     """Times the OpenMP oracle (bit-identical to the single-threaded one) on a bounded sample of
     the workload: a `rows`-row slab of the size-wide reference scene, `rows` chosen so the whole
     run fits the budget.  Returns (Gcell/s, cores, sample description, ms per step)."""
     import numpy as np
     from oracle.oracle_py import Oracle
-    o = Oracle(openmp=True)
-    cores = o.threads
+    o = Oracle(openmp=openmp)
+    cores = o.threads if openmp else 1
     consts = o.derive_consts(float(size), size)
 
-    scene = o.create_scene(size, size)
+    scene = (o if openmp else Oracle(openmp=True)).create_scene(size, size)      # scene generation is not what is timed
 
     def slab(rows):                       # central rows: the lake sits in the middle of the map
         a = (size - rows) // 2
@@ -172,7 +172,8 @@ def cpu_oracle_throughput(size: int, steps: int, warmup: int, budget_s: float):
     o.step(t, f, v, consts, steps)
     dt = time.perf_counter() - t0
     gcells = rows * size * steps / dt / 1e9
-    sample = f"{size}x{rows} central-row slab of the {size}x{size} reference scene, {steps} steps after {warmup} warm-up, OpenMP oracle on {cores} threads"
+    sample = (f"{size}x{rows} central-row slab of the {size}x{size} reference scene, {steps} steps after {warmup} warm-up, "
+              + (f"OpenMP oracle on {cores} threads" if openmp else "single-threaded oracle"))
     return gcells, cores, sample, dt / steps * 1e3
 
 
@@ -382,6 +383,12 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, cores, sample, _ = cpu_oracle_throughput(W, 4, 1, budget_s=20.0)
         cpu = {"value": val, "unit": "Gcell-updates/s", "cores": cores, "kind": "port", "sample": sample}
+        # the parity reference itself, one core
+        try:
+            v1, _, s1, _ = cpu_oracle_throughput(W, 2, 1, budget_s=6.0, openmp=False)
+            cpu["single_thread"] = {"value": v1, "unit": "Gcell-updates/s", "cores": 1, "sample": s1}
+        except Exception as e:                      # an extra figure must never cost the bench line
+            cpu["single_thread"] = {"error": str(e)}
 
     if rank == 0:
         line = {
