@@ -248,10 +248,6 @@ tws_status run_block_band_strip(tws_sim* s, int k) {
   };
   if (s->up.present) peer_planes(s->up, (long long)TWS_HALO_ROWS + s->up.rows, ed.up);          // my top rows -> its bottom halo
   if (s->down.present) peer_planes(s->down, (long long)TWS_HALO_ROWS - g.rows, ed.down);        // my bottom rows -> its top halo
-  static const int dbg = [] { const char* e = getenv("TWS_EDGE_DEBUG"); return e ? atoi(e) : 0; }();   // timing experiments only
-  if (dbg & 1) { ed.wait_up = nullptr; ed.wait_down = nullptr; }
-  if (dbg & 2) { ed.up_end = 0; ed.down_begin = INT32_MAX; }
-  if (dbg & 4) { ed.post_up = nullptr; ed.post_down = nullptr; }
   TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));          // a tws_halo_refresh on the edge stream comes first
   TWS_CUDA(s, launch_band(k, g, s->planes, s->tma_stream[src], src, s->consts, 0, g.rows, s->st_main, s->ctrl->sched_main, 0, &ed, e_top, e_bot));
   s->launches += 1;
