@@ -21,7 +21,10 @@ def build(force: bool = False) -> None:
     """make -C oracle (also builds oracle/_ref when /root/reference is present)."""
     need = force or not (ORACLE_DIR / "libtws_oracle.so").exists() or not (ORACLE_DIR / "libtws_oracle_omp.so").exists() \
         or (ORACLE_DIR / "tws_oracle.cpp").stat().st_mtime > (ORACLE_DIR / "libtws_oracle.so").stat().st_mtime
-    ref_missing = Path("/root/reference/terrainwatersim/source/math").is_dir() and not (ORACLE_DIR / "_ref" / "libtws_ref_terrain.so").exists()
+    ref_missing = Path("/root/reference/terrainwatersim/source/math").is_dir() and not (
+        (ORACLE_DIR / "_ref" / "libtws_ref_terrain.so").exists() and (ORACLE_DIR / "_ref" / "libtws_ref_step.so").exists()
+        and (ORACLE_DIR / "_ref" / "libtws_ref_step.so").stat().st_mtime >= max(
+            (ORACLE_DIR / f).stat().st_mtime for f in ("ref_step_driver.cpp", "ref_shim/glsl.h", "ref_shim/glsl_prep.py")))
     if need or ref_missing:
         res = subprocess.run(["make", "-C", str(ORACLE_DIR)] + (["-B"] if force else []), capture_output=True, text=True)
         if res.returncode != 0:
@@ -112,6 +115,48 @@ class Oracle:
 
     def float_to_half_bits(self, f: float) -> int:
         return int(self.lib.tws_oracle_float_to_half(f))
+
+
+class RefStep:
+    """ctypes wrapper of oracle/_ref/libtws_ref_step.so: the reference's OWN flowUpdate.comp / flowApply.comp /
+    waterBrush.comp compiled from /root/reference through the GLSL shim (oracle/ref_step_driver.cpp).  Same
+    texture layouts and call shapes as Oracle, minus the extensions the reference does not have.  Defined where
+    the reference is: it dispatches res/16 (step) and res/32 (brush) whole groups (Terrain.cpp:167,258,264)."""
+
+    PATH = ORACLE_DIR / "_ref" / "libtws_ref_step.so"
+
+    def __init__(self):
+        build()
+        if not self.PATH.exists():
+            raise FileNotFoundError(str(self.PATH))
+        self.lib = C.CDLL(str(self.PATH))
+        L = self.lib
+        L.tws_ref_step_threads.restype = C.c_int
+        L.tws_ref_step.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.tws_ref_flow_update.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tws_ref_flow_apply.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tws_ref_brush.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
+
+    def step(self, terrain, flow, flowmap, consts, n=1):
+        H, W = terrain.shape[:2]
+        assert terrain.dtype == np.float32 and flow.dtype == np.float32 and flowmap.dtype == np.float16
+        assert terrain.flags.c_contiguous and flow.flags.c_contiguous and flowmap.flags.c_contiguous
+        c = np.ascontiguousarray(consts, np.float32)
+        self.lib.tws_ref_step(W, H, _fp(terrain), _fp(flow), _fp(flowmap), _fp(c), n)
+
+    def flow_update(self, terrain, flow, consts):
+        H, W = terrain.shape[:2]
+        c = np.ascontiguousarray(consts, np.float32)
+        self.lib.tws_ref_flow_update(W, H, _fp(terrain), _fp(flow), _fp(c))
+
+    def flow_apply(self, terrain, flow, flowmap, consts):
+        H, W = terrain.shape[:2]
+        c = np.ascontiguousarray(consts, np.float32)
+        self.lib.tws_ref_flow_apply(W, H, _fp(terrain), _fp(flow), _fp(flowmap), _fp(c))
+
+    def brush(self, terrain, cx, cy, intensity, size_sq=32.0):
+        H, W = terrain.shape[:2]
+        self.lib.tws_ref_brush(W, H, _fp(terrain), cx, cy, intensity, size_sq)
 
 
 def new_state(terrain_h: np.ndarray, water_d: np.ndarray):

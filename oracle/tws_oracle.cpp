@@ -4,15 +4,20 @@
 // and bench.py's cpu_baseline / --impl reference legs may load it.  The product
 // (terrainwatersim_b200 / libtws.so) never links, imports or calls anything here.
 //
-// PARITY STATUS.  The reference holds no test, golden vector or CPU path for the step
-//  and its GLSL cannot run here (no GL 4.3 context): the step part
-// of this oracle is therefore "parity unpinned" — it is a line-for-line transcription
-// of the two compute shaders with the implementation-defined pieces pinned as stated
-// below, checked only against hand-derived micro cases and invariants (tests/).  The
-// terrain/initial-state part (create_reference_scene) IS pinned: it is checked
-// bit-for-bit against the reference's own NoiseGenerator.cpp/Random.cpp compiled from
-// /root/reference (oracle/Makefile -> oracle/_ref/) and against the hashes that build
-// produced (tests/golden/).
+// PARITY STATUS: PINNED AGAINST THE REFERENCE'S OWN SOURCE.  The reference holds no test or
+// golden vector for the step and its GLSL cannot run on a GPU here (no
+// GL 4.3 context), but its shader SOURCE can be compiled: oracle/Makefile target `ref_step`
+// builds /root/reference/terrainwatersim/shader/{flowUpdate,flowApply,waterBrush}.comp, from
+// where they lie, through the GLSL language shim oracle/ref_shim/glsl.h into
+// oracle/_ref/libtws_ref_step.so, and tests/test_oracle.py asserts this transcription
+// bit-equal to it — BASELINE config 1 (walled + open, 1000 steps), config 2 (brush, 1000
+// steps), random 16-multiple grids pass by pass, micro cases on work-group seams, fp16 ties —
+// and tests/golden/ holds the hashes the reference shaders produced.  What stays PINNED BY
+// ASSUMPTION because the GL driver, not the repository, decides it, is listed below (the shim
+// makes the same four choices).  The terrain/initial-state part (create_reference_scene) is
+// checked bit-for-bit against the reference's own NoiseGenerator.cpp/Random.cpp compiled from
+// /root/reference (oracle/_ref/libtws_ref_terrain.so).  Ragged grid sizes (not multiples of
+// 16) and the EXT modes are outside what the reference defines and are oracle-defined.
 //
 // Pinned arithmetic contract: IEEE binary32, every + - * / a single
 // rounding evaluated in the order written in the shader, NO fused multiply-add

@@ -1,8 +1,10 @@
-"""Pins the CPU oracle (oracle/tws_oracle.cpp): against the reference's own terrain generator
-compiled from /root/reference (oracle/_ref), against hand-derived micro cases of the two
-shader passes (flowUpdate.comp / flowApply.comp), against invariants of the scheme and
-against the committed golden hashes.  The reference has no tests for this path
- — these are the replacement pins of SURVEY.md §8c."""
+"""Pins the CPU oracle (oracle/tws_oracle.cpp): against the reference's own simulation shaders
+(flowUpdate.comp / flowApply.comp / waterBrush.comp compiled from /root/reference through the GLSL shim
+into oracle/_ref/libtws_ref_step.so) and the reference's own terrain generator (oracle/_ref/
+libtws_ref_terrain.so), bit for bit; against hand-derived micro cases of the two shader passes; against
+invariants of the scheme and against the committed golden hashes (which make_goldens.py takes from the
+reference-compiled shaders).  The reference has no tests for this path — these are the
+replacement pins of SURVEY.md §8c."""
 import ctypes as C
 import json
 from pathlib import Path
@@ -10,7 +12,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from oracle.oracle_py import dam_break, new_state
+from oracle.oracle_py import RefStep, dam_break, new_state
 
 ROOT = Path(__file__).resolve().parent.parent
 GOLD = json.loads((ROOT / "tests" / "golden" / "goldens.json").read_text())
@@ -319,3 +321,130 @@ def test_cxx_oracle_equals_an_independent_numpy_transcription(oracle, W, H, seed
         assert np.array_equal(v1.view(np.uint16), v2.view(np.uint16)), f"FlowMap differs at step {step}"
         scaled += int(((t2[..., 3] == 0) & (f2.sum(axis=-1) > 0)).sum())
     assert scaled > 0                      # the clamp branch (:58-59) was exercised
+
+
+# ---- the step pinned against the reference's OWN shader source ----------------------------------------------------
+# oracle/_ref/libtws_ref_step.so = /root/reference/terrainwatersim/shader/{flowUpdate,flowApply,waterBrush}.comp compiled
+# where they lie (oracle/Makefile `ref_step`; language shim oracle/ref_shim/glsl.h; host side oracle/ref_step_driver.cpp
+# dispatching res/16 x res/16 groups of 18 x 18 invocations as Terrain.cpp:258,264 and res/32 groups of 32 x 32 for the
+# brush as Terrain.cpp:167).  The reference is defined on multiples of 16 (32 for the brush) only.
+@pytest.fixture(scope="session")
+def ref_step(built):
+    try:
+        return RefStep()
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/libtws_ref_step.so not built (needs /root/reference)")
+
+
+def _bits_equal(a, b):
+    return all(np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(a, b))
+
+
+def _hashes(o, t, f, v):
+    return {"d": f"{o.fnv1a64(np.ascontiguousarray(t[..., 3])):016x}", "F": f"{o.fnv1a64(f):016x}", "v": f"{o.fnv1a64(v.view(np.uint16)):016x}"}
+
+
+@pytest.mark.parametrize("name,rim", [("dam256_walled", True), ("dam256_open", False)])
+def test_reference_shaders_config1_1000_steps(oracle_omp, ref_step, name, rim):
+    """BASELINE config 1 through the reference's shaders: equal to the oracle and to the goldens at 1/10/100/1000 steps."""
+    assert GOLD["step_goldens_source"].startswith("reference shaders")
+    h, d = dam_break(256, rim=rim)
+    c = oracle_omp.derive_consts(256.0, 256)
+    a, b = new_state(h, d), new_state(h, d)
+    done = 0
+    for n in (1, 10, 100, 1000):
+        ref_step.step(*a, c, n - done)
+        oracle_omp.step(*b, c, n - done)
+        done = n
+        assert _bits_equal(a, b), f"oracle differs from the reference shaders after {n} steps"
+        g = GOLD[name][str(n)]
+        assert _hashes(oracle_omp, *a) == {k: g[k] for k in ("d", "F", "v")}
+
+
+def test_reference_shaders_config2_scene_with_brush_1000_steps(oracle_omp, ref_step):
+    """BASELINE config 2 (1024^2 reference scene, brush at (512,512) with 100/60 before every step, Scene.cpp:356-363)
+    through the reference's brush and step shaders."""
+    c = oracle_omp.derive_consts(1024.0, 1024)
+    scene = oracle_omp.create_scene(1024)
+    a = (scene.copy(), np.zeros((1024, 1024, 4), np.float32), np.zeros((1024, 1024, 2), np.float16))
+    b = (scene.copy(), np.zeros((1024, 1024, 4), np.float32), np.zeros((1024, 1024, 2), np.float16))
+    inten = np.float32(100.0 / 60.0)
+    done = 0
+    for n in (1, 10, 100, 1000):
+        for _ in range(n - done):
+            ref_step.brush(a[0], 512.0, 512.0, inten, 32.0)
+            ref_step.step(*a, c, 1)
+            oracle_omp.brush(b[0], 512.0, 512.0, inten, 32.0)
+            oracle_omp.step(*b, c, 1)
+        done = n
+        assert _bits_equal(a, b), f"oracle differs from the reference shaders after {n} steps"
+        g = GOLD["scene1024_brush"][str(n)]
+        assert _hashes(oracle_omp, *a) == {k: g[k] for k in ("d", "F", "v")}
+
+
+@pytest.mark.parametrize("W,H,seed", [(16, 16, 1), (64, 32, 2), (32, 96, 3), (160, 128, 4), (256, 64, 5)])
+def test_reference_shaders_random_grids_every_pass(oracle, ref_step, W, H, seed):
+    """Rough random scenes (dry, wet and draining cells, huge gradients at the open edge), random per-step constants, each of
+    the two dispatches compared separately, brush with fractional / off-grid centres and negative intensity in between."""
+    rng = np.random.default_rng(seed)
+    h = (rng.random((H, W)) * 8).astype(np.float32)
+    d = (rng.random((H, W)) * 4 * (rng.random((H, W)) > 0.4)).astype(np.float32)
+    c = np.float32([0.9 + 0.1 * rng.random(), 0.05 + 0.3 * rng.random(), 0.01 + 0.3 * rng.random()])
+    a, b = new_state(h, d), new_state(h, d)
+    scaled = 0
+    for step in range(60):
+        if step % 7 == 3 and W % 32 == 0 and H % 32 == 0:
+            cx, cy = float(rng.uniform(-4, W + 4)), float(rng.uniform(-4, H + 4))
+            inten, size_sq = float(rng.uniform(-1, 3)), float(rng.uniform(1, 60))
+            ref_step.brush(a[0], cx, cy, inten, size_sq)
+            oracle.brush(b[0], cx, cy, inten, size_sq)
+            assert _bits_equal(a, b), f"brush differs at step {step}"
+        ref_step.flow_update(a[0], a[1], c)
+        oracle.flow_update(b[0], b[1], c)
+        assert _bits_equal(a, b), f"flowUpdate differs at step {step}"
+        scaled += int((((a[1].sum(axis=-1) * c[2]) >= a[0][..., 3]) & (a[1].sum(axis=-1) > 0)).sum())
+        ref_step.flow_apply(a[0], a[1], a[2], c)
+        oracle.flow_apply(b[0], b[1], b[2], c)
+        assert _bits_equal(a, b), f"flowApply differs at step {step}"
+    assert scaled > 0                      # the clamp branch (flowUpdate.comp:58-59) was exercised
+    assert np.isfinite(a[0]).all()
+
+
+def test_reference_shaders_micro_cases_and_group_seams(oracle, ref_step):
+    """Hand-checkable values through the reference's shaders: a single wet cell placed ON a work-group seam (x = 15 | 16)
+    and one in the grid corner (the open boundary: out-of-range imageLoad = 0), flowUpdate.comp:44-59."""
+    c = np.float32([1.0, 0.125, 0.5])
+    h = np.zeros((32, 32), np.float32)
+    d = np.zeros((32, 32), np.float32)
+    d[15, 16] = 2.0
+    d[0, 0] = 1.0
+    h[0, 0] = 3.0
+    t, f, v = new_state(h, d)
+    ref_step.flow_update(t, f, c)
+    assert np.array_equal(f[15, 16], np.float32([0.25, 0.25, 0.25, 0.25]))
+    assert np.array_equal(f[0, 0], np.float32([0.5, 0.5, 0.5, 0.5]))          # (4 - 0) * 0.125 towards exterior and dry neighbours
+    ref_step.flow_apply(t, f, v, c)
+    assert t[15, 16, 3] == f32(1.5) and t[15, 15, 3] == t[15, 17, 3] == t[14, 16, 3] == t[16, 16, 3] == f32(0.125)
+    assert t[0, 0, 3] == 0.0 and t[0, 1, 3] == f32(0.25) and t[1, 0, 3] == f32(0.25)     # half of the corner's water left the grid
+    assert np.array_equal(v[15, 17], np.float16([-0.25, 0]))
+    t2, f2, v2 = new_state(h, d)
+    oracle.step(t2, f2, v2, c, 1)
+    assert _bits_equal((t, f, v), (t2, f2, v2))
+
+
+def test_reference_shader_rg16f_store_rounds_to_nearest_even(oracle, ref_step):
+    """FlowMap values straddling fp16 rounding ties, subnormals and overflow, produced through flowApply.comp:45-52."""
+    vals = np.float32([1.00048828125, 1.0009765625 + 0.00048828125, 2049.0, 2051.0, 65519.9, 65520.0, 70000.0, 6e-8, 2.98e-8,
+                       2.9802322e-8, 3e-8, 6.1035156e-5, 6.0975552e-5, 0.1, 1e-3, 3.14159])
+    W = H = 16
+    t, f, v = new_state(np.zeros((H, W), np.float32), np.zeros((H, W), np.float32))
+    for i, x in enumerate(vals):                  # cell (1, i%..): inflow from its -X neighbour's +X flux = x  ->  v.x = -(x)
+        f[2 * (i // 4) + 1, 4 * (i % 4), 0] = x   # +X outflow of the left neighbour
+    t2, f2, v2 = t.copy(), f.copy(), v.copy()
+    c = np.float32([1.0, 0.0, 0.0])
+    ref_step.flow_apply(t, f, v, c)
+    oracle.flow_apply(t2, f2, v2, c)
+    assert np.array_equal(v.view(np.uint16), v2.view(np.uint16))
+    with np.errstate(over="ignore"):
+        for i, x in enumerate(vals):
+            assert v[2 * (i // 4) + 1, 4 * (i % 4) + 1, 0].view(np.uint16) == np.float16(-x).view(np.uint16)
