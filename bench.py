@@ -45,7 +45,10 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the end-to-end leg (default min(steps, 40))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--verify-strips", action="store_true", help="compare the strips with a whole-grid run on rank 0 (small sizes)")
+    ap.add_argument("--verify-strips", action="store_true", help="also compare the strips of the BENCH grid with a whole-grid run on rank 0 (small --size only)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (BASELINE config 4: 32768^2 split over the ranks)")
+    ap.add_argument("--strong-size", type=int, default=32768)
+    ap.add_argument("--strong-steps", type=int, default=48)
     return ap.parse_args()
 
 
@@ -70,38 +73,105 @@ def ncu_traffic_per_launch(kernel_tag: str):
         return None
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+class _NvmlCtypes:
+    """The five NVML calls the sampler needs, straight from libnvidia-ml.so.1 (used when the pynvml module is missing)."""
+    NVML_CLOCK_SM = 1
 
-    def __init__(self, device_index: int, period_s: float = 0.02):
+    def __init__(self):
+        import ctypes as C
+        self.C = C
+        self.lib = C.CDLL("libnvidia-ml.so.1")
+        if self.lib.nvmlInit_v2() != 0:
+            raise RuntimeError("nvmlInit_v2 failed")
+
+    def handle(self, index):
+        h = self.C.c_void_p()
+        if self.lib.nvmlDeviceGetHandleByIndex_v2(self.C.c_uint(index), self.C.byref(h)) != 0:
+            raise RuntimeError("nvmlDeviceGetHandleByIndex_v2 failed")
+        return h
+
+    def _uint(self, fn, h, *args):
+        v = self.C.c_uint(0)
+        if fn(h, *args, self.C.byref(v)) != 0:
+            raise RuntimeError("nvml call failed")
+        return int(v.value)
+
+    def max_sm(self, h):
+        return self._uint(self.lib.nvmlDeviceGetMaxClockInfo, h, self.C.c_int(self.NVML_CLOCK_SM))
+
+    def sm(self, h):
+        return self._uint(self.lib.nvmlDeviceGetClockInfo, h, self.C.c_int(self.NVML_CLOCK_SM))
+
+    def reasons(self, h):
+        v = self.C.c_ulonglong(0)
+        fn = getattr(self.lib, "nvmlDeviceGetCurrentClocksEventReasons", None) or self.lib.nvmlDeviceGetCurrentClocksThrottleReasons
+        if fn(h, self.C.byref(v)) != 0:
+            raise RuntimeError("nvml reasons failed")
+        return int(v.value)
+
+
+class _NvmlModule:
+    def __init__(self):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+
+    def handle(self, index):
+        return self.nv.nvmlDeviceGetHandleByIndex(index)
+
+    def max_sm(self, h):
+        return int(self.nv.nvmlDeviceGetMaxClockInfo(h, self.nv.NVML_CLOCK_SM))
+
+    def sm(self, h):
+        return int(self.nv.nvmlDeviceGetClockInfo(h, self.nv.NVML_CLOCK_SM))
+
+    def reasons(self, h):
+        try:
+            return int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            return int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+
+
+def _physical_gpu_index(local: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            pass
+    return local
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML (pynvml, else ctypes on libnvidia-ml.so.1) while the GPU is under
+    the bench load.  `mark(t0, t1)` windows are the regions whose samples count."""
+
+    def __init__(self, device_index: int, period_s: float = 0.004):
         super().__init__(daemon=True)
         self.period = period_s
         self.samples = []           # (t, sm_mhz, reasons_bitmask)
         self.max_mhz = None
         self._stop_evt = threading.Event()
         self.ok = False
-        try:
-            import pynvml
-            self.nv = pynvml
-            pynvml.nvmlInit()
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
-            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.ok = True
-        except Exception:
-            self.ok = False
+        self.via = None
+        self.windows = []
+        for name, cls in (("pynvml", _NvmlModule), ("ctypes:libnvidia-ml.so.1", _NvmlCtypes)):
+            try:
+                self.nv = cls()
+                self.h = self.nv.handle(_physical_gpu_index(device_index))
+                self.max_mhz = self.nv.max_sm(self.h)
+                self.nv.sm(self.h)
+                self.ok, self.via = True, name
+                break
+            except Exception:
+                continue
 
     def run(self):
         if not self.ok:
             return
-        nv = self.nv
         while not self._stop_evt.is_set():
             try:
-                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                except Exception:
-                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.samples.append((time.perf_counter(), mhz, reasons))
+                self.samples.append((time.perf_counter(), self.nv.sm(self.h), self.nv.reasons(self.h)))
             except Exception:
                 pass
             time.sleep(self.period)
@@ -109,21 +179,25 @@ class ClockSampler(threading.Thread):
     def stop(self):
         self._stop_evt.set()
 
-    def summary(self, t0: float, t1: float):
-        if not self.ok or not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
-        inside = [s for s in self.samples if t0 <= s[0] <= t1]
-        note = None
-        if len(inside) < 3:
-            inside = self.samples
-            note = "timed region shorter than 3 samples: includes warm-up samples"
+    def mark(self, t0: float, t1: float):
+        self.windows.append((t0, t1))
+
+    def inside(self):
+        return [s for s in self.samples if any(a <= s[0] <= b for a, b in self.windows)]
+
+    def summary(self, note=None):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "note": "NVML not reachable (neither pynvml nor libnvidia-ml.so.1)"}
+        inside = self.inside()
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "note": "no NVML sample fell into the loaded region", "via": self.via}
         names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
                  0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
         mask = 0
-        for s in inside:
-            mask |= s[2]
+        for smp in inside:
+            mask |= smp[2]
         reasons = sorted(n for b, n in names.items() if mask & b and n != "gpu_idle")
-        out = {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(inside)}
+        out = {"sm_mhz": statistics.median(smp[1] for smp in inside), "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(inside), "via": self.via}
         if note:
             out["note"] = note
         return out
@@ -139,6 +213,13 @@ def dist_env():
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores (the ONLY place bench.py uses oracle/)
 # --------------------------------------------------------------------------------------------------
+def host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_oracle_throughput(size: int, steps: int, warmup: int, budget_s: float, openmp: bool = True):
     """Times the OpenMP oracle (bit-identical to the single-threaded one) on a bounded sample of
     the workload: a `rows`-row slab of the size-wide reference scene, `rows` chosen so the whole
@@ -146,6 +227,10 @@ def cpu_oracle_throughput(size: int, steps: int, warmup: int, budget_s: float, o
     import numpy as np
     from oracle.oracle_py import Oracle
     o = Oracle(openmp=openmp)
+    if openmp:
+        # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: set the thread count explicitly so the host
+        # baseline uses every core this process may run on, whatever the launcher exported
+        o.set_threads(host_cores())
     cores = o.threads if openmp else 1
     consts = o.derive_consts(float(size), size)
 
@@ -181,6 +266,7 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(host_cores())      # before libgomp initialises (torchrun exports 1)
     val, cores, sample, ms = cpu_oracle_throughput(args.size, args.steps, args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": "Gcell-updates/s per sim step (fp32)", "value": val, "unit": "Gcell-updates/s",
@@ -238,15 +324,6 @@ def run_b200(args):
     backend = {"unfused": tws.BACKEND_UNFUSED, "fused": tws.BACKEND_FUSED, "tb": tws.BACKEND_FUSED_TB,
                "stream": tws.BACKEND_STREAM_TB, "band": tws.BACKEND_BAND_TB}[args.backend]
     k = args.tb if args.backend in ("tb", "stream", "band") else 1
-    sim = tws.Terrain(W, height=Hg, rows=plan.rows(rank), backend=backend, temporal_block=k, device=local)
-    tws.connect_strips(sim, plan, rank)
-    # weak scaling: every GPU's strip is the SAME W x W scene (the generator's terrain is periodic, so the tiles join
-    # seamlessly) — per-GPU work is then fixed as N grows, which a scene stretched over W x (W*N) is not
-    tile = 0 if args.strong else W
-    sim.CreateHeightmapFromNoiseAndResetSim(tileHeight=tile)
-    sim.sync()
-    cells_global = W * Hg
-    cells_local = W * sim.rows
 
     def barrier():
         if world > 1:
@@ -267,44 +344,71 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    def timed_steps(sim, steps, warmup):
+        """warm-up, then exactly `steps` steps between barrier + synchronize; device time (CUDA events on the library's
+        launching stream), max over ranks.  Returns (ms, local launches, wall t0, wall t1)."""
+        barrier()
+        sim.step(warmup)
+        sim.sync()
+        barrier()
+        l0 = sim.kernel_launches()
+        t0 = time.perf_counter()
+        sim.step(steps)
+        sim.sync()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        ms_dev = sim.elapsed_ms()
+        launches_local = sim.kernel_launches() - l0
+        barrier()
+        return max_over_ranks(ms_dev), ms_dev, launches_local, t0, t1
+
+    sim = tws.Terrain(W, height=Hg, rows=plan.rows(rank), backend=backend, temporal_block=k, device=local)
+    tws.connect_strips(sim, plan, rank)
+    # weak scaling: every GPU's strip is the SAME W x W scene (the generator's terrain is periodic, so the tiles join
+    # seamlessly) — per-GPU work is then fixed as N grows, which a scene stretched over W x (W*N) is not
+    tile = 0 if args.strong else W
+    sim.CreateHeightmapFromNoiseAndResetSim(tileHeight=tile)
+    sim.sync()
+    cells_global = W * Hg
+    cells_local = W * sim.rows
+
     sampler = ClockSampler(local)
     sampler.start()
     # ---- device-resident throughput: warm-up, then exactly K steps ---------------------------------
-    barrier()
-    sim.step(args.warmup)
-    sim.sync()
-    barrier()
-    l0 = sim.kernel_launches()
-    t_wall0 = time.perf_counter()
-    sim.step(args.steps)
-    sim.sync()
-    torch.cuda.synchronize()
-    t_wall1 = time.perf_counter()
-    ms_dev = sim.elapsed_ms()                  # CUDA events on the library's launching stream
-    launches_local = sim.kernel_launches() - l0
-    barrier()
-    sampler.stop()
-    ms = max_over_ranks(ms_dev)
+    ms, ms_dev, launches_local, t_wall0, t_wall1 = timed_steps(sim, args.steps, args.warmup)
+    sampler.mark(t_wall0, t_wall1)
     launches = int(sum_over_ranks(float(launches_local)))
     value = cells_global * args.steps / (ms * 1e-3) / 1e9
-    clocks = sampler.summary(t_wall0, t_wall1)
+    clock_note = None
+    if len(sampler.inside()) < 5 and sampler.ok:
+        # the timed region was shorter than a handful of NVML samples (e.g. --steps 20 = 4 ms): keep the SAME kernel running,
+        # untimed, until the sampler has seen the GPU under this load
+        t0 = time.perf_counter()
+        extra = 0
+        while len(sampler.inside()) + len([x for x in sampler.samples if x[0] >= t0]) < 8 and time.perf_counter() - t0 < 2.0:
+            sim.step(4 * k)
+            sim.sync()
+            extra += 4 * k
+        sampler.mark(t0, time.perf_counter())
+        clock_note = f"timed region ({ms:.1f} ms) shorter than the NVML sampling period x 5: samples include {extra} further untimed steps of the same kernel run right after it"
+    clocks = sampler.summary(clock_note)
 
     # ---- roofline of the dominant kernel (the step kernel; all launches in the region are it) -------
     peak, peak_src = measured_peak_gbs()
-    if world == 1:
-        n_step_launches = launches_local
-    else:
-        n_step_launches = (args.steps + k - 1) // k      # per rank: interior launch count
     launch_ms = ms_dev / max(1, (args.steps + k - 1) // k)
     algo_bytes_per_launch = ALGO_BYTES_PER_CELL_UPDATE * cells_local * min(k, args.steps)
     achieved = algo_bytes_per_launch / (launch_ms * 1e-3) / 1e9
     tag = {"unfused": "unfused", "fused": "fused_k1", "tb": f"fused_k{k}", "stream": f"stream_k{k}", "band": f"band_k{k}"}[args.backend]
     traffic = ncu_traffic_per_launch(tag) if (W == 8192 and sim.rows == 8192) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/traffic.json (ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this grid, committed; not re-measured in this run)" if traffic else None,
+                "dram_frac": (traffic / (launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "kernel": {"unfused": "unfused_update_kernel+unfused_apply_kernel", "stream": "stream_step_kernel", "band": "band_step_kernel"}.get(args.backend, "fused_step_kernel"),
                 "peak_source": peak_src, "algorithmic_bytes_per_cell_update": ALGO_BYTES_PER_CELL_UPDATE,
                 "cell_updates_per_launch": cells_local * min(k, args.steps), "avg_launch_ms": launch_ms,
-                "note": "achieved = 48 B x cell-updates per launch / launch time; with temporal blocking (k steps per HBM round trip) real DRAM traffic is ~48/k B per cell-update, so frac may exceed 1"}
+                "note": "frac = 48 B x cell-updates per launch / launch time / peak (SURVEY 8d basis); with temporal blocking (k steps per HBM round trip) "
+                        "real DRAM traffic is ~48/k B per cell-update, so frac may exceed 1; dram_frac = ncu DRAM bytes per launch / launch time / peak is the "
+                        "share of the HBM bandwidth the kernel really uses"}
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------
     e2e = None
@@ -347,40 +451,106 @@ def run_b200(args):
                "d2h_bytes_per_step": int(sum_over_ranks(cells_local * 8.0)), "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
                "gpu_launches": int(timings["host_launches"]),
                "serial_calls_value": cells_global * n_e2e / timings["serial"] / 1e9,
+               "pcie_gbs_per_gpu": {"h2d": cells_local * 4.0 * n_e2e / dt / 1e9, "d2h": cells_local * 8.0 * n_e2e / dt / 1e9},
                "what": "per step ONE call tws_step_host(water_in, water_out, velocity_out) with pinned host buffers: 4 B/cell up, 8 B/cell down, "
-                       "uploaded / stepped / read back in row bands on three streams so both PCIe directions overlap the kernels; terrain and flux "
+                       "uploaded / stepped / read back in row bands on three streams so both PCIe directions overlap the kernels (strips included: the "
+                       "uploaded edge rows are pushed to the neighbours first, the output edge rows last); terrain and flux "
                        "stay device-resident as in the reference (its state never leaves the GPU). serial_calls_value = the same frame as "
                        "tws_upload + tws_step(1) + 2 x tws_readback (no overlap)"}
+        del d_host, v_host
 
-    # ---- strips vs whole grid (tests) ------------------------------------------------------------------
-    if args.verify_strips and world > 1:
-        n_chk = 12
+    def strips_match_whole_grid(s, pl, Wc, Hc, tile_c, n_chk):
+        """resets the strips `s` (one per rank) to the reference scene, puts a brush across the first seam, steps n_chk and
+        compares depth, flux and velocity bit for bit with a whole-grid run of the UNFUSED kernels on rank 0."""
         barrier()                                    # strips must be quiescent around a reset
-        sim.CreateHeightmapFromNoiseAndResetSim(tileHeight=tile)
+        s.CreateHeightmapFromNoiseAndResetSim(tileHeight=tile_c)
         barrier()
-        sim.inject_brush(W / 2 + 0.25, plan.rows(1)[0] - 0.5, 5.0, 64.0)
-        sim.step(n_chk)
-        sim.sync()
-        mine = (sim.readback(tws.FIELD_WATER), sim.readback(tws.FIELD_FLUX), sim.readback(tws.FIELD_VELOCITY).view(np.uint16))
+        s.inject_brush(Wc / 2 + 0.25, pl.rows(1)[0] - 0.5, 5.0, 64.0)
+        s.step(n_chk)
+        s.sync()
+        mine = (s.readback(tws.FIELD_WATER), s.readback(tws.FIELD_FLUX), s.readback(tws.FIELD_VELOCITY).view(np.uint16))
         parts = [None] * world if rank == 0 else None
         dist.gather_object(mine, parts, dst=0)
+        ok = True
         if rank == 0:
-            with tws.Terrain(W, height=Hg, backend=tws.BACKEND_UNFUSED, device=local) as whole:
-                whole.CreateHeightmapFromNoiseAndResetSim(tileHeight=tile)
-                whole.inject_brush(W / 2 + 0.25, plan.rows(1)[0] - 0.5, 5.0, 64.0)
+            with tws.Terrain(Wc, height=Hc, backend=tws.BACKEND_UNFUSED, device=local) as whole:
+                whole.CreateHeightmapFromNoiseAndResetSim(tileHeight=tile_c)
+                whole.inject_brush(Wc / 2 + 0.25, pl.rows(1)[0] - 0.5, 5.0, 64.0)
                 whole.step(n_chk)
                 ok = (np.array_equal(np.concatenate([p[0] for p in parts]).view(np.uint32), whole.readback(tws.FIELD_WATER).view(np.uint32))
                       and np.array_equal(np.concatenate([p[1] for p in parts]).view(np.uint32), whole.readback(tws.FIELD_FLUX).view(np.uint32))
                       and np.array_equal(np.concatenate([p[2] for p in parts]), whole.readback(tws.FIELD_VELOCITY).view(np.uint16)))
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.broadcast(flag, src=0)
+        return bool(flag.item())
+
+    # ---- strips vs whole grid on the bench grid itself (tests, small --size) ---------------------------
+    if args.verify_strips and world > 1:
+        ok = strips_match_whole_grid(sim, plan, W, Hg, tile, 12)
+        if rank == 0:
             print("STRIPS_VERIFIED" if ok else "STRIPS_MISMATCH", flush=True)
-            if not ok:
-                raise SystemExit(3)
-        dist.barrier()
+        if not ok:
+            raise SystemExit(3)
 
     sim.close()
+    del sim
+    torch.cuda.empty_cache()
+
+    # ---- multi-GPU parity, every run with N > 1: 1024 x 1024*N, band kernel k = 4, brush across a seam -----
+    strips_verified = None
+    if world > 1:
+        Wv, Hv = 1024, 1024 * world
+        planv = tws.plan_strips(Hv, world)
+        simv = tws.Terrain(Wv, height=Hv, rows=planv.rows(rank), backend=tws.BACKEND_BAND_TB, temporal_block=4, device=local)
+        tws.connect_strips(simv, planv, rank)
+        strips_verified = strips_match_whole_grid(simv, planv, Wv, Hv, 0, 24)
+        simv.close()
+        if rank == 0 and not strips_verified:
+            print("STRIPS_MISMATCH (1024 x 1024*N parity run)", flush=True)
+        if not strips_verified:
+            raise SystemExit(3)
+
+    # ---- strong scaling, BASELINE config 4: the SAME 32768^2 grid on 1 GPU (T1, rank 0) and split over the N ranks (TN) ----
+    strong = None
+    if not args.no_strong and not args.strong:
+        S = args.strong_size
+        ks = 4
+        need_gb = 48.0 * S * S / 1e9 + 4.0
+        free_gb = torch.cuda.mem_get_info()[0] / 1e9
+        if free_gb < need_gb:
+            strong = {"skipped": f"{S}x{S} needs {need_gb:.0f} GB on one GPU for T1, {free_gb:.0f} GB free"}
+        else:
+            t1_ms = None
+            if rank == 0:
+                with tws.Terrain(S, backend=tws.BACKEND_BAND_TB, temporal_block=ks, device=local) as whole:
+                    whole.CreateHeightmapFromNoiseAndResetSim()
+                    whole.sync()
+                    whole.step(8); whole.sync()
+                    whole.step(args.strong_steps); whole.sync()
+                    t1_ms = whole.elapsed_ms() / args.strong_steps
+                torch.cuda.empty_cache()
+            if world > 1:
+                t = torch.tensor([t1_ms or 0.0], dtype=torch.float64, device="cuda")
+                dist.broadcast(t, src=0)
+                t1_ms = float(t.item())
+                plans = tws.plan_strips(S, world)
+                sims = tws.Terrain(S, height=S, rows=plans.rows(rank), backend=tws.BACKEND_BAND_TB, temporal_block=ks, device=local)
+                tws.connect_strips(sims, plans, rank)
+                sims.CreateHeightmapFromNoiseAndResetSim()
+                sims.sync()
+                tn_total, _, _, _, _ = timed_steps(sims, args.strong_steps, 8)
+                tn_ms = tn_total / args.strong_steps
+                sims.close()
+            else:
+                tn_ms = t1_ms
+            strong = {"grid": [S, S], "workload": f"BASELINE config 4: {S}x{S} reference scene, band kernel k={ks}, {world} row strip(s)",
+                      "steps": args.strong_steps, "t1_ms_per_step": t1_ms, "tn_ms_per_step": tn_ms,
+                      "value": S * S / (tn_ms * 1e-3) / 1e9, "unit": "Gcell-updates/s", "t1_value": S * S / (t1_ms * 1e-3) / 1e9,
+                      "efficiency": t1_ms / (world * tn_ms),
+                      "definition": "T1 / (N x TN), both measured in THIS run: T1 = the whole grid on rank 0's GPU alone, TN = the same grid as N strips, device time, max over ranks (SURVEY 8d)"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         val, cores, sample, _ = cpu_oracle_throughput(W, 4, 1, budget_s=20.0)
         cpu = {"value": val, "unit": "Gcell-updates/s", "cores": cores, "kind": "port", "sample": sample}
         # SURVEY 8(d): the parity reference itself, one core
@@ -396,7 +566,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "per_gpu_value": value / world,
+            "per_gpu_value": value / world, "strips_verified": strips_verified, "strong": strong,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

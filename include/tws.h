@@ -124,7 +124,8 @@ const char* tws_version(void);
 int32_t     tws_abi_version(void);
 
 /* Reference defaults: 1024x1024, world 1024, 60 steps/s, damping 0.98, acceleration 10
- * (Terrain.cpp:21-30), open boundary, FUSED backend, whole grid on device 0. */
+ * (Terrain.cpp:21-30), open boundary, whole grid on device 0, backend TWS_BACKEND_AUTO (resolved at tws_create
+ * from the cell count — several steps per launch; see tws_backend_in_use). */
 void tws_default_params(tws_params* p);
 
 /* Replaces Terrain::Terrain + texture creation (Terrain.cpp:21-121,200-238): allocates
@@ -197,11 +198,26 @@ tws_status tws_sync(tws_sim* s);
  * cell_area_inv_time_scaled it is the volume the last step drained off the map
  * (flowApply.comp:38-41 with the exterior reading 0).  Synchronises. */
 tws_status tws_boundary_outflow(tws_sim* s, double* flux_sum);
+/* EXTENSION, the ledger that works with k steps per launch: the step kernels themselves accumulate, in fp64 and in every
+ * sub-step, (outflow across the edge of the global grid) x cell_area_inv_time_scaled from the lanes that own an edge
+ * cell.  `volume` = the water volume that has left the map through this sim's part of the edge since creation, the last
+ * tws_reset_reference_scene or tws_boundary_outflow_reset (always 0 with TWS_BOUNDARY_CLOSED).  With rain and
+ * evaporation off, total_volume(t) + this == total_volume(0) up to fp32 rounding of the depth updates; SURVEY.md 8d
+ * config 5 closes the ledger V0 + sources - outflow with it.  The sum order of the atomics is not fixed: equal to the
+ * oracle's per-step fp64 sum to ~1e-15 relative, not bitwise.  tws_boundary_outflow_accumulated synchronises. */
+tws_status tws_boundary_outflow_accumulated(tws_sim* s, double* volume);
+tws_status tws_boundary_outflow_reset(tws_sim* s);
 
 /* Device-side timing of the most recent tws_step/tws_advance batch (CUDA events on the
  * launching stream; replaces gl::TimerQuery around PerformSimulationStep,
  * Scene.cpp:362-364).  Synchronises on the end event. */
 tws_status tws_elapsed_ms(tws_sim* s, float* ms);
+/* The same without ever blocking — what the reference does: its gl::TimerQuery is double buffered
+ * (TimerQuery.cpp:29-72) and Scene::Update reads LAST frame's result (Scene.cpp:337-342).  Batches
+ * alternate between two event pairs; this returns the time of the newest batch the GPU has already
+ * finished (the most recent one, else the one before) and its 0-based index through batch_index (may
+ * be NULL); TWS_ERR_STATE when neither has finished yet.  Call it once per frame after tws_advance. */
+tws_status tws_elapsed_ms_nowait(tws_sim* s, float* ms, uint64_t* batch_index);
 /* Number of kernels launched by this sim since creation (kernels inside a replayed batch graph count). */
 uint64_t   tws_kernel_launches(const tws_sim* s);
 /* Frame scheduler: a whole-grid sim captures each batch size n (2..64) of tws_step / tws_advance as
@@ -239,8 +255,15 @@ tws_status tws_halo_refresh(tws_sim* s);
  * tws_gl_register takes the GL names of the renderer's two textures (flow_map_tex may be 0) and
  * registers them with cudaGraphicsGLRegisterImage; the renderer's GL context must be current
  * on the calling thread (otherwise TWS_ERR_CUDA).  tws_gl_publish writes (r = terrain,
- * g = b = 0.3, a = water) plus the mip chain and the flow vectors into them.  Whole grids
- * only (a strip returns TWS_ERR_UNSUPPORTED).
+ * g = b = 0.3, a = water) plus the mip chain and the flow vectors into them.  tws_gl_* are for
+ * whole grids (the renderer samples one texture; a strip returns TWS_ERR_UNSUPPORTED).
+ *
+ * Strips (multi-GPU): tws_publish_packed / tws_publish_mips work per strip.  A strip builds the levels
+ * it can filter from its own rows alone — level l needs row_begin and the row count to be multiples
+ * of 2^l (plan_strips cuts on multiples of 8 rows: levels 0..3 at least); `levels` returns how many.
+ * Level l of a strip is max(1, width >> l) x (rows >> l) texels = rows [row_begin >> l, row_end >> l)
+ * of the whole grid's level l, bit for bit.  The renderer's GPU gathers the strips' last common level
+ * (1/64 of level 0 at l = 3) and filters the remaining small levels itself with the rule below.
  *
  * The same data without GL: tws_publish_packed packs level 0 and the flow map into device
  * buffers the library owns; tws_publish_mips additionally builds the mip chain, level L

@@ -54,6 +54,10 @@ class Terrain {
   void Sync() { check(tws_sync(sim_)); }
   double TotalVolume() { double v = 0; check(tws_total_volume(sim_, &v)); return v; }
   float SimulationTimeMs() { float ms = 0; check(tws_elapsed_ms(sim_, &ms)); return ms; }   // "Simulation Time" stat, Scene.cpp:341-342
+  // the reference's own way (gl::TimerQuery, read one frame late, never blocks): false while no timed batch has finished
+  bool SimulationTimeMsNoWait(float* ms) { const tws_status st = tws_elapsed_ms_nowait(sim_, ms, nullptr); if (st == TWS_ERR_STATE) return false; check(st); return true; }
+  // EXT mass ledger: volume that left the map through the open boundary (accumulated inside the step kernels)
+  double BoundaryOutflowVolume() { double v = 0; check(tws_boundary_outflow_accumulated(sim_, &v)); return v; }
   void Upload(tws_field f, const void* host, size_t bytes) { check(tws_upload(sim_, f, host, bytes)); }
   void Readback(tws_field f, void* host, size_t bytes) { check(tws_readback(sim_, f, host, bytes)); }
   // Renderer hand-off (Terrain.cpp:272-276,288,323-330): the renderer keeps owning TerrainInfo (RGBA32F, full

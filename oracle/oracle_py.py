@@ -60,6 +60,9 @@ class Oracle:
     def threads(self) -> int:
         return int(self.lib.tws_oracle_threads())
 
+    def set_threads(self, n: int) -> None:
+        self.lib.tws_oracle_set_threads(int(n))
+
     def derive_consts(self, world_size=1024.0, res=1024, steps_per_second=60.0, damping=0.98, acceleration=10.0) -> np.ndarray:
         out = np.zeros(3, np.float32)
         self.lib.tws_oracle_derive_consts(world_size, res, steps_per_second, damping, acceleration, _fp(out))

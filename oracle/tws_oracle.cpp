@@ -252,6 +252,15 @@ int tws_oracle_threads(void) {
 #endif
 }
 
+// Thread count of the OpenMP build (no effect on the single-threaded one); results do not depend on it.
+void tws_oracle_set_threads(int n) {
+#if defined(_OPENMP)
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 // Terrain.cpp:175-198 — the three per-step constants, including the float/double mix:
 // dt = (double)(1.0f / stepsPerSecond); cellDistance = world / (float)res (float);
 // friction = powf(damping, (float)dt); accel = (float)(dt * a * cellDistance) with the

@@ -100,7 +100,10 @@ SYMBOLS = {
     "tws_total_volume": (C.c_int, [_SIM, C.POINTER(C.c_double)]),
     "tws_sync": (C.c_int, [_SIM]),
     "tws_boundary_outflow": (C.c_int, [_SIM, C.POINTER(C.c_double)]),
+    "tws_boundary_outflow_accumulated": (C.c_int, [_SIM, C.POINTER(C.c_double)]),
+    "tws_boundary_outflow_reset": (C.c_int, [_SIM]),
     "tws_elapsed_ms": (C.c_int, [_SIM, C.POINTER(C.c_float)]),
+    "tws_elapsed_ms_nowait": (C.c_int, [_SIM, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "tws_kernel_launches": (C.c_uint64, [_SIM]),
     "tws_graph_replays": (C.c_uint64, [_SIM]),
     "tws_backend_in_use": (C.c_int, [_SIM, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -32,6 +32,9 @@ cudaError_t launch_brush(const Geom& g, float* d, float cx, float cy, float inte
   const double lo_x = floor((double)cx - rad), hi_x = ceil((double)cx + rad);
   const double lo_y = floor((double)cy - rad), hi_y = ceil((double)cy + rad);
   const int row_lo = g.row0 - (g.has_up ? TWS_HALO_ROWS : 0), row_hi = g.row0 + g.rows + (g.has_down ? TWS_HALO_ROWS : 0);
+  // a box that misses the stored rows / columns entirely adds 0 everywhere, like the reference's whole-grid pass; decided in
+  // double BEFORE any cast to int (a finite centre beyond INT_MAX must not reach the casts)
+  if (lo_x > (double)g.W - 1 || hi_x < 0.0 || lo_y > (double)row_hi - 1 || hi_y < (double)row_lo) return cudaSuccess;
   const int x0 = (int)fmax(lo_x, 0.0), x1 = (int)fmin(hi_x, (double)g.W - 1);
   const int y0 = (int)fmax(lo_y, (double)row_lo), y1 = (int)fmin(hi_y, (double)row_hi - 1);
   if (x1 < x0 || y1 < y0) return cudaSuccess;

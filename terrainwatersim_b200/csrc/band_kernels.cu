@@ -82,32 +82,6 @@ struct BandRow {       // per-row context (the lane's column offset and store ma
 #ifndef TWS_BAND_SPLIT
 #define TWS_BAND_SPLIT 1
 #endif
-// Suspend-time hint (ns) of the barrier waits: a waiting warp sleeps in hardware until its phase completes (or the
-// hint runs out) instead of coming back after the short default time limit and re-issuing the wait loop — waiting
-// warps share their scheduler with working ones, so every spin instruction is taken from a row that could make
-// progress.  0: no hint.
-#ifndef TWS_BAND_SUSPEND_NS
-#define TWS_BAND_SUSPEND_NS 0
-#endif
-#ifndef TWS_BAND_SUSPEND_FULL_NS
-#define TWS_BAND_SUSPEND_FULL_NS 0
-#endif
-// wait for a TMA landing buffer (same loop as mbar_wait, optionally with a suspend-time hint)
-__device__ __forceinline__ void band_wait_full(uint64_t* bar, uint32_t parity) {
-#if TWS_BAND_SUSPEND_FULL_NS
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)TWS_BAND_SUSPEND_FULL_NS) : "memory");
-  } while (!done);
-#else
-  mbar_wait(bar, parity);
-#endif
-}
 struct GroupSync {
   uint32_t bar;        // shared address of the group's mbarrier
   uint32_t phase;      // parity of the phase the next wait() waits for
@@ -118,25 +92,26 @@ struct GroupSync {
     if (!TWS_BAND_SPLIT) wait_now();
   }
   __device__ __forceinline__ void wait() { if (TWS_BAND_SPLIT) wait_now(); }
+  // Four polls per pass of the loop, and only a failed fourth one pays for the hang guard: a waiting warp shares its
+  // scheduler with working ones, so every instruction of the wait loop is taken from a row that could make progress
+  // (round-1 ncu: ~6 wake-ups per wait at 7 instructions each were 30 % of all issued instructions; now 2 per poll
+  // + 4 per four polls).  try_wait itself suspends the warp for a hardware-defined time before it reports failure.
   __device__ __forceinline__ void wait_now() {
+#define TWS_GS_POLL "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra TWS_GS_DONE;\n"
     asm volatile(
         "{\n"
         ".reg .pred p, q;\n"
         ".reg .u32 n;\n"
         "mov.u32 n, 0;\n"
         "TWS_GS_LOOP:\n"
-#if TWS_BAND_SUSPEND_NS
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-#else
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-#endif
-        "@p bra TWS_GS_DONE;\n"
+        TWS_GS_POLL TWS_GS_POLL TWS_GS_POLL TWS_GS_POLL
         "add.u32 n, n, 1;\n"
-        "setp.gt.u32 q, n, 16777216;\n"
+        "setp.gt.u32 q, n, 4194304;\n"
         "@q trap;\n"                                      // a barrier that never completes is a bug; a trap beats a hung GPU
         "bra TWS_GS_LOOP;\n"
         "TWS_GS_DONE:\n"
-        "}\n" ::"r"(bar), "r"(phase), "r"((uint32_t)TWS_BAND_SUSPEND_NS) : "memory");
+        "}\n" ::"r"(bar), "r"(phase) : "memory");
+#undef TWS_GS_POLL
     phase ^= 1u;
   }
 };
@@ -295,7 +270,8 @@ __device__ __forceinline__ void band_flux(GroupSync& sy, const uint32_t (&up)[R]
         if (EDGE && !(rc[q].row_in && (unsigned)(gx + i) < (unsigned)g.W)) { pfx[i] = 0.f; pfy[i] = 0.f; }
       }
     }
-    if (LAST && rc[q].store && st_col && !TWS_DBG_NOSTORE) {
+    if (EDGE && rc[q].store && st_col) ledger_add(c, g, gx, rc[q].gy, fx[q], fy[q], fz[q], fw[q]);   // every sub-step, owner lanes only
+    if (LAST && rc[q].store && st_col) {
       st4(out.F[0] + rc[q].go, fx[q]); st4(out.F[1] + rc[q].go, fy[q]); st4(out.F[2] + rc[q].go, fz[q]); st4(out.F[3] + rc[q].go, fw[q]);
       if (edge.nlev_edge) push_flux(edge, rc[q].gy - g.row0, rc[q].go, fx[q], fy[q], fz[q], fw[q]);
     }
@@ -384,7 +360,7 @@ __device__ __forceinline__ void band_depth(GroupSync& sy, const uint32_t (&up)[R
         float vy0, vy1, vy2, vy3;                                                     // vy = (iY1 - fz) - (iY0 - fw), :46
         upk(sub2(sub2(lo2(iy1[q]), lo2(fz[q])), sub2(lo2(iy0[q]), lo2(fw[q]))), vy0, vy1);
         upk(sub2(sub2(hi2(iy1[q]), hi2(fz[q])), sub2(hi2(iy0[q]), hi2(fw[q]))), vy2, vy3);
-        if (rc[q].store && st_col && !TWS_DBG_NOSTORE) {
+        if (rc[q].store && st_col) {
           st4(out.d + rc[q].go, nd[q]);
           if (edge.nlev_edge) push_depth(edge, rc[q].gy - g.row0, rc[q].go, nd[q]);
           *reinterpret_cast<uint4*>(out.v + rc[q].go) =
@@ -422,7 +398,7 @@ __device__ __forceinline__ void band_depth(GroupSync& sy, const uint32_t (&up)[R
   if (LAST) {
 #pragma unroll
     for (int q = 0; q < R; ++q)
-      if (rc[q].store && st_col && !TWS_DBG_NOSTORE) {
+      if (rc[q].store && st_col) {
         st4(out.d + rc[q].go, make_float4(nds[q][0], nds[q][1], nds[q][2], nds[q][3]));
         if (edge.nlev_edge) push_depth(edge, rc[q].gy - g.row0, rc[q].go, make_float4(nds[q][0], nds[q][1], nds[q][2], nds[q][3]));
         *reinterpret_cast<uint4*>(out.v + rc[q].go) = make_uint4(nvs[q][0], nvs[q][1], nvs[q][2], nvs[q][3]);
@@ -470,6 +446,9 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
   const uint32_t xch = smem_u32(gsm + BR * LAND + lane * 4);
   const int pw = (NW - 1 - warp) < HP ? (NW - 1 - warp) : HP;     // half-passes the last row gets inside its own band
   const bool carrier = pw < HP;
+  // the half-pass before which a carrier switches to the row it parked one band ago (0: never).  Pinned in a register:
+  // left to the compiler it is re-derived from the warp index (8 instructions) in front of every half-pass
+  const uint32_t swap_at = keep_u32(carrier ? (uint32_t)(pw + 1) : 0u);
   float* park = gsm + BR * LAND + C::NSLOT * XROW + (carrier ? warp - (NW - C::NC) : 0) * LAND + lane * 4;
 
   // Exchange slots.  Band row o = q*NW + warp uses slot o, except the last NDB rows of a band, which
@@ -545,7 +524,7 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
     const bool st_col = lane * 4 >= HX && lane * 4 < HX + OX && gx < g.pitch;
 
     auto issue = [&](int i0) {                            // one lane: land the warp's R rows of the band starting at piece row i0
-      if (!TWS_DBG_NOFENCE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(full, (uint32_t)(R * LAND * sizeof(float)));
 #pragma unroll
       for (int q = 0; q < R; ++q) {
@@ -600,7 +579,7 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
       // ---- half-pass 0: registers <- landing buffers; publish H; prefetch this warp's rows of the next band ----
       const bool loaded = i0 + warp < N;
       if (loaded) {
-        band_wait_full(full, parity);
+        mbar_wait(full, parity);
         parity ^= 1u;
 #pragma unroll
         for (int q = 0; q < R; ++q) {
@@ -621,9 +600,8 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
 
       // ---- the 2K computing half-passes.  Carriers switch their last row once, before half-pass pw + 1;
       // rows on the grid edge take the masked variants ----
-      const int swap_at = carrier ? pw + 1 : 0;
 #pragma unroll 1
-      for (int lv = 1; lv < K; ++lv) {
+      for (uint32_t lv = 1; lv < (uint32_t)K; ++lv) {
         if (2 * lv - 1 == swap_at) swap_rows(j);
         if (plain) band_flux<R, SXW, false, false>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
         else band_flux<R, SXW, true, false>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);

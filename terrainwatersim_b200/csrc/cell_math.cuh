@@ -69,6 +69,31 @@ __device__ __forceinline__ float apply_cell(float depth, float fx, float fy, flo
   return nd;
 }
 
+// EXT mass ledger (Control::outflow_acc).  Called by the ONE lane that owns the four cells (gx0..gx0+3, gy) as output
+// cells of its piece / tile, with their final outflow of a sub-step: adds what points out of the global grid — +X at
+// x = W-1, -X at x = 0, +Y on the last global row, -Y on row 0 — times areaInv.  Interior lanes leave after four compares.
+__device__ __forceinline__ void ledger_add(const StepConsts& c, const Geom& g, int gx0, int gy, const float4& fx, const float4& fy,
+                                           const float4& fz, const float4& fw) {
+  if (c.ledger == nullptr || (unsigned)gy >= (unsigned)g.Hg) return;
+  const bool ytop = gy == 0, ybot = gy == g.Hg - 1;
+  if (!(ytop || ybot || gx0 == 0 || gx0 + 3 >= g.W - 1)) return;
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = gx0 + i;
+    if ((unsigned)x >= (unsigned)g.W) continue;
+    const float px = i == 0 ? fx.x : (i == 1 ? fx.y : (i == 2 ? fx.z : fx.w));
+    const float py = i == 0 ? fy.x : (i == 1 ? fy.y : (i == 2 ? fy.z : fy.w));
+    const float pz = i == 0 ? fz.x : (i == 1 ? fz.y : (i == 2 ? fz.z : fz.w));
+    const float pw = i == 0 ? fw.x : (i == 1 ? fw.y : (i == 2 ? fw.z : fw.w));
+    if (x == g.W - 1) s += (double)px;
+    if (x == 0) s += (double)py;
+    if (ybot) s += (double)pz;
+    if (ytop) s += (double)pw;
+  }
+  if (s != 0.0) atomicAdd(c.ledger, s * (double)c.area_inv);
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float x, float y) {                  // rg16f store, :52
   const __half2 h = __floats2half2_rn(x, y);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -248,13 +273,6 @@ __device__ __forceinline__ uint32_t keep_u32(uint32_t v) {       // pins a value
 #define TWS_STREAM_HX_MIN 8    // tuning: widen the x halo so that the output columns of a strip start on a 64 / 128 B boundary
 #endif
 constexpr int stream_hx(int K) { return ((2 * K + 3) / 4) * 4 > TWS_STREAM_HX_MIN ? ((2 * K + 3) / 4) * 4 : TWS_STREAM_HX_MIN; }
-
-#ifndef TWS_DBG_NOFENCE
-#define TWS_DBG_NOFENCE 0   // tuning experiment only
-#endif
-#ifndef TWS_DBG_NOSTORE
-#define TWS_DBG_NOSTORE 0   // tuning experiment only: 1 drops the HBM stores (wrong results)
-#endif
 
 struct FusedOut {          // plane pointers at local row 0
   float* d; float* F[4]; uint32_t* v;

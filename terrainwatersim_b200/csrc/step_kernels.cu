@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256) unfused_update_kernel(Geom g, const float
     if (gx >= g.W) { pfx[i] = 0.f; pfy[i] = 0.f; pfz[i] = 0.f; pfw[i] = 0.f; }      // pad columns stay 0
   }
   st4(Fxp + o, fx); st4(Fxm + o, fy); st4(Fyp + o, fz); st4(Fym + o, fw);
+  ledger_add(c, g, x, gy, fx, fy, fz, fw);
   }
 }
 
@@ -239,10 +240,11 @@ __device__ __forceinline__ void flux_level(float* __restrict__ st, const int (&o
     sts4_if(live, sFym + oq, fw[q]);
     sts_if(live && lane == 31, sFxp + oq + 3, fx[q].w);        // for lane 0 of the next warp
     sts_if(live && lane == 0, sFxm + oq, fy[q].x);             // for lane 31 of the previous warp
-    if (LAST) {
+    if (EDGE || LAST) {
       bool store = valid[q] && x >= C::HX && x < C::HX + C::OX && r >= C::HY && r < C::HY + C::OY;
       if (EDGE) store = store && tc.ly0 + r < g.rows && gx0 < g.pitch;
-      if (store) {
+      if (EDGE && store) ledger_add(c, g, gx0, gy, fx[q], fy[q], fz[q], fw[q]);      // every sub-step, the tile's own output cells only
+      if (LAST && store) {
         const size_t go = (size_t)((long long)(tc.ly0 + r) * g.pitch) + gx0;
         st4(out.F[0] + go, fx[q]); st4(out.F[1] + go, fy[q]); st4(out.F[2] + go, fz[q]); st4(out.F[3] + go, fw[q]);
       }

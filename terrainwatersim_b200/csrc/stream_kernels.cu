@@ -275,7 +275,8 @@ __device__ __forceinline__ void stream_flux(const uint32_t up, const uint32_t dn
     }
     sts4(me + 4 * SXW + 512 * q, fz[q]);         // plane 1: +Y outflow, read by the row below
     sts4(me + 8 * SXW + 512 * q, fw[q]);         // plane 2: -Y outflow, read by the row above
-    if (LAST && rc.store && rc.st[q] && !TWS_DBG_NOSTORE) {
+    if (EDGE && rc.store && rc.st[q]) ledger_add(c, g, rc.gx[q], rc.gy, fx[q], fy[q], fz[q], fw[q]);       // every sub-step, owner lanes only
+    if (LAST && rc.store && rc.st[q]) {
       st4(out.F[0] + rc.go[q], fx[q]); st4(out.F[1] + rc.go[q], fy[q]); st4(out.F[2] + rc.go[q], fz[q]); st4(out.F[3] + rc.go[q], fw[q]);
     }
   }
@@ -322,7 +323,7 @@ __device__ __forceinline__ void stream_depth(const uint32_t up, const uint32_t d
     if (!LAST) {
       d[q] = make_float4(nd[0], nd[1], nd[2], nd[3]);
       sts4(me + 512 * q, add4(d[q], h[q]));
-    } else if (rc.store && rc.st[q] && !TWS_DBG_NOSTORE) {
+    } else if (rc.store && rc.st[q]) {
       st4(out.d + rc.go[q], make_float4(nd[0], nd[1], nd[2], nd[3]));
       *reinterpret_cast<uint4*>(out.v + rc.go[q]) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
     }
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
     __syncthreads();
 
     auto issue = [&](int y) {                             // one lane: land row y in this warp's buffer
-      if (!TWS_DBG_NOFENCE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&full[warp], (uint32_t)(LAND * sizeof(float)));
       const int ty = y + tma_y_bias;
       tma_load_2d(land, &tm_h, sx0, ty, &full[warp]);

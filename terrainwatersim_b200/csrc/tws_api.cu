@@ -27,6 +27,7 @@ struct Peer {
   bool ipc = false;          // opened with cudaIpcOpenMemHandle (must be closed)
   uint8_t* slab = nullptr;   // peer slab base, addressable from this device
   int rows = 0;              // peer's own rows
+  int device = -1;           // CUDA device the peer's slab lives on
   Planes planes{};
   Control* ctrl = nullptr;
 };
@@ -53,7 +54,11 @@ struct tws_sim {
   cudaStream_t st_main = nullptr, st_edge = nullptr;
   cudaStream_t st_h2d = nullptr, st_d2h = nullptr;      // tws_step_host: upload / readback streams (created on first use)
   std::vector<cudaEvent_t> band_ev;                     // tws_step_host: [2b] band b uploaded, [2b+1] band b computed
-  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_main = nullptr, ev_edge = nullptr;
+  // Timing of step batches, double buffered like gl::TimerQuery (TimerQuery.cpp:29-72): batch i records into pair i & 1,
+  // so the pair of the batch BEFORE the most recent one can be read without waiting for the GPU.
+  cudaEvent_t ev_pair[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [pair][0 = start, 1 = stop]
+  uint64_t batches_timed = 0;        // batches recorded so far; the most recent one used pair (batches_timed - 1) & 1
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_main = nullptr, ev_edge = nullptr;   // ev_start / ev_stop: aliases of the current pair
   bool timed = false;
   uint64_t launches = 0;
   uint32_t epoch = 0;                // exchange blocks completed (same on all strips)
@@ -138,6 +143,7 @@ void derive_constants(tws_sim* s) {
   s->consts.evap_step = (float)(s->step_length * p.evaporation_rate);     // EXT
   s->consts.ext_sources = (s->consts.rain_step != 0.0f || s->consts.evap_step != 0.0f) ? 1 : 0;
   s->consts.closed = (p.boundary == TWS_BOUNDARY_CLOSED) ? 1 : 0;
+  s->consts.ledger = (s->ctrl != nullptr && !s->consts.closed) ? &s->ctrl->outflow_acc : nullptr;   // EXT mass ledger
 }
 
 bool bad_float(float v) { return !(v == v) || std::isinf(v); }
@@ -272,7 +278,16 @@ tws_status run_block_stream(tws_sim* s, int k) {
     s->cur = 1 - src;
     return TWS_OK;
   }
-  if (stream_impl(s) == 1) return run_block_band_strip(s, k);
+  if (stream_impl(s) == 1) {
+    // In the one-launch form every warp group that holds an edge piece polls the neighbour's flag.  When the neighbour
+    // shares THIS GPU (a test configuration) and the grid is so wide that the edge pieces could occupy every resident
+    // group, the neighbour's launch might never get an SM: such strips use the two-stream form below instead.
+    const bool shared_gpu = (s->up.present && s->up.device == s->prm.device) || (s->down.present && s->down.device == s->prm.device);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->prm.device);
+    const int nstrips_x = (g.W + 111) / 112;             // 112 output columns per column strip of the band kernel
+    if (!(shared_gpu && 2 * nstrips_x >= sms)) return run_block_band_strip(s, k);
+  }
   int e_top = g.has_up ? TWS_HALO_ROWS : 0, e_bot = g.has_down ? TWS_HALO_ROWS : 0;
   if (e_top + e_bot >= g.rows) { e_top = g.rows; e_bot = 0; }
   const int i0 = e_top, i1 = g.rows - e_bot;
@@ -396,10 +411,18 @@ tws_status run_batch_graph(tws_sim* s, int n, int K, bool* done) {
   return TWS_OK;
 }
 
+// the next batch records into the other event pair
+void next_timing_pair(tws_sim* s) {
+  const int p = (int)(s->batches_timed & 1u);
+  s->ev_start = s->ev_pair[p][0]; s->ev_stop = s->ev_pair[p][1];
+  s->batches_timed += 1;
+}
+
 tws_status run_steps(tws_sim* s, int n) {
   const Geom& g = s->geom;
   const bool strip = g.has_up || g.has_down;
   if (strip && !s->connected) return fail(s, TWS_ERR_STATE, "strip sim stepped before tws_halo_connect");
+  next_timing_pair(s);
   TWS_CUDA(s, cudaEventRecord(s->ev_start, s->st_main));
   const int K = (s->prm.backend == TWS_BACKEND_FUSED_TB || is_stream_backend(s->prm.backend)) ? s->K : 1;
   if (!strip && s->use_graphs && n >= 2 && n <= 64) {
@@ -516,12 +539,16 @@ tws_status tws_create(const tws_params* p, tws_sim** out) {
     return bail(e == cudaErrorMemoryAllocation ? TWS_ERR_NOMEM : TWS_ERR_CUDA, std::string("tws_create: cudaMalloc of the state slab failed: ") + cudaGetErrorString(e));
   layout_planes(s->slab, g.pitch, g.rows, &s->planes, nullptr, nullptr);
   s->ctrl = (Control*)s->slab;
+  derive_constants(s);                                  // now that the control block exists: the ledger pointer
   if ((e = cudaStreamCreateWithFlags(&s->st_main, cudaStreamNonBlocking)) != cudaSuccess) return bail(TWS_ERR_CUDA, cudaGetErrorString(e));
   int lo_prio = 0, hi_prio = 0;
   cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
   if ((e = cudaStreamCreateWithPriority(&s->st_edge, cudaStreamNonBlocking, hi_prio)) != cudaSuccess) return bail(TWS_ERR_CUDA, cudaGetErrorString(e));
-  if ((e = cudaEventCreate(&s->ev_start)) != cudaSuccess || (e = cudaEventCreate(&s->ev_stop)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&s->ev_main, cudaEventDisableTiming)) != cudaSuccess ||
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j)
+      if ((e = cudaEventCreate(&s->ev_pair[i][j])) != cudaSuccess) return bail(TWS_ERR_CUDA, cudaGetErrorString(e));
+  s->ev_start = s->ev_pair[0][0]; s->ev_stop = s->ev_pair[0][1];
+  if ((e = cudaEventCreateWithFlags(&s->ev_main, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&s->ev_edge, cudaEventDisableTiming)) != cudaSuccess)
     return bail(TWS_ERR_CUDA, cudaGetErrorString(e));
   if ((e = cudaMemsetAsync(s->slab, 0, s->slab_bytes, s->st_main)) != cudaSuccess) return bail(TWS_ERR_CUDA, cudaGetErrorString(e));
@@ -551,8 +578,9 @@ tws_status tws_destroy(tws_sim* s) {
   if (s->packed_info) cudaFree(s->packed_info);
   if (s->packed_flow) cudaFree(s->packed_flow);
   if (s->slab) cudaFree(s->slab);
-  if (s->ev_start) cudaEventDestroy(s->ev_start);
-  if (s->ev_stop) cudaEventDestroy(s->ev_stop);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j)
+      if (s->ev_pair[i][j]) cudaEventDestroy(s->ev_pair[i][j]);
   if (s->ev_main) cudaEventDestroy(s->ev_main);
   if (s->ev_edge) cudaEventDestroy(s->ev_edge);
   if (s->st_main) cudaStreamDestroy(s->st_main);
@@ -672,6 +700,13 @@ tws_status tws_reset_reference_scene_tiled(tws_sim* s, uint32_t seed, float heig
   DeviceGuard guard(s->prm.device);
   tws_status r = sync_all(s);
   if (r) return r;
+  if ((s->geom.has_up || s->geom.has_down) && s->connected) {
+    // the scene kernel also writes this strip's halo rows: the neighbours' pushes of the last block must have landed
+    // first (as in tws_inject_brush).  All strips must be reset together, with no step in between.
+    TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));
+    TWS_CUDA(s, launch_wait_flags(s->ctrl, s->geom.has_up, s->geom.has_down, s->epoch, s->st_main));
+    s->launches += 1;
+  }
   if (!s->white_dev) TWS_CUDA(s, cudaMalloc(&s->white_dev, 4096 * sizeof(float)));
   float table[4096];
   white_noise_table(seed, table);
@@ -682,6 +717,7 @@ tws_status tws_reset_reference_scene_tiled(tws_sim* s, uint32_t seed, float heig
   TWS_CUDA(s, launch_scene(s->geom, s->planes, s->cur, s->white_dev, height_scale, lo, hi, persistence, tile_h, s->st_main));
   s->launches += 1;
   s->accumulator = 0.0;
+  TWS_CUDA(s, cudaMemsetAsync(&s->ctrl->outflow_acc, 0, sizeof(double), s->st_main));   // a new scene starts a new ledger
   TWS_CUDA(s, cudaStreamSynchronize(s->st_main));
   return TWS_OK;
 }
@@ -734,11 +770,11 @@ tws_status tws_step_host(tws_sim* s, const float* water_in, float* water_out, vo
   const Geom& g = s->geom;
   const size_t plane_bytes = (size_t)g.W * g.rows * 4;
   const bool strip = g.has_up || g.has_down;
-  if (strip || s->prm.backend == TWS_BACKEND_UNFUSED) {
-    // Strips exchange halos between GPUs and the unfused baseline updates in place: no band pipeline.
+  if (strip && !s->connected) return fail(s, TWS_ERR_STATE, "strip sim stepped before tws_halo_connect");
+  if (s->prm.backend == TWS_BACKEND_UNFUSED) {
+    // The unfused baseline updates in place: no band pipeline.
     tws_status r = TWS_OK;
     if (water_in) { r = transfer(s, TWS_FIELD_WATER, (void*)water_in, plane_bytes, true); if (r) return r; }
-    if (strip && water_in) { r = tws_halo_refresh(s); if (r) return r; }
     r = run_steps(s, 1); if (r) return r;
     if (water_out) { r = transfer(s, TWS_FIELD_WATER, water_out, plane_bytes, false); if (r) return r; }
     if (velocity_out) { r = transfer(s, TWS_FIELD_VELOCITY, velocity_out, plane_bytes, false); if (r) return r; }
@@ -756,7 +792,7 @@ tws_status tws_step_host(tws_sim* s, const float* water_in, float* water_out, vo
   const size_t want_rows = std::max<size_t>(1, ((size_t)8 << 20) / ((size_t)g.W * 4));
   const int band_units = (int)std::max<size_t>(stream_be ? 8 : 1, (want_rows + unit - 1) / unit);
   const int nb = (units + band_units - 1) / band_units;
-  while ((int)s->band_ev.size() < 2 * nb) {
+  while ((int)s->band_ev.size() < 2 * nb + 1) {
     cudaEvent_t e;
     TWS_CUDA(s, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     s->band_ev.push_back(e);
@@ -768,22 +804,65 @@ tws_status tws_step_host(tws_sim* s, const float* water_in, float* water_out, vo
     *r0 = std::min(g.rows, b * band_units * unit);
     *r1 = std::min(g.rows, (b + 1) * band_units * unit);
   };
+  auto upload_rows = [&](int r0, int r1) -> cudaError_t {
+    if (r1 <= r0) return cudaSuccess;
+    return cudaMemcpy2DAsync(s->planes.d[src] + off + (size_t)r0 * g.pitch, dp, (const uint8_t*)water_in + (size_t)r0 * hp, hp, hp,
+                             (size_t)(r1 - r0), cudaMemcpyHostToDevice, s->st_h2d);
+  };
+  next_timing_pair(s);
   TWS_CUDA(s, cudaEventRecord(s->ev_start, s->st_main));
   // uploads and readbacks start after everything already queued on the main stream
   TWS_CUDA(s, cudaStreamWaitEvent(s->st_h2d, s->ev_start, 0));
   TWS_CUDA(s, cudaStreamWaitEvent(s->st_d2h, s->ev_start, 0));
+  // Strips: the neighbours compute their edge rows from OUR new edge rows.  Those go up first and are pushed into the
+  // neighbours' halo rows (peer stores over NVLink) behind a flag, so that by the time a neighbour's first / last band is
+  // due its halo is long there; the rest of the water layer follows band by band.
+  int e_top = 0, e_bot = 0;                               // own rows already uploaded ahead of the bands
+  if (strip && water_in) {
+    const int P = std::min(TWS_HALO_ROWS, g.rows);
+    e_top = s->up.present ? P : 0;
+    e_bot = s->down.present ? std::min(P, g.rows - e_top) : 0;
+    TWS_CUDA(s, upload_rows(0, e_top));
+    TWS_CUDA(s, upload_rows(g.rows - e_bot, g.rows));
+    if (e_top < P && s->up.present) e_top = 0;            // (cannot happen: a strip has >= 8 rows)
+    TWS_CUDA(s, cudaEventRecord(s->band_ev[2 * nb], s->st_h2d));
+    TWS_CUDA(s, cudaStreamWaitEvent(s->st_edge, s->ev_main, 0));
+    TWS_CUDA(s, cudaStreamWaitEvent(s->st_edge, s->band_ev[2 * nb], 0));
+    // the bottom rows were uploaded as rows [rows - e_bot, rows): the push takes the outermost P rows of each side
+    RowCopy c[2]; int n = 0;
+    auto fill = [&](const Peer& peer, bool to_up) {
+      RowCopy rc{};
+      rc.src[0] = s->planes.d[src]; rc.dst[0] = peer.planes.d[src];
+      rc.nplanes = 1; rc.nrows = P; rc.pitch = g.pitch;
+      if (to_up) { rc.src_row = TWS_HALO_ROWS; rc.dst_row = TWS_HALO_ROWS + peer.rows; }
+      else { rc.src_row = TWS_HALO_ROWS + g.rows - P; rc.dst_row = TWS_HALO_ROWS - P; }
+      return rc;
+    };
+    if (s->up.present) c[n++] = fill(s->up, true);
+    if (s->down.present) c[n++] = fill(s->down, false);
+    // a short strip's two pushes may both need rows of the other side's upload: both uploads are behind the one event
+    TWS_CUDA(s, launch_row_copy(c[0], c[n - 1], n, s->st_edge));
+    s->launches += 1;
+    r = post_and_count(s, s->st_edge);
+    if (r) return r;
+    TWS_CUDA(s, cudaEventRecord(s->ev_edge, s->st_edge));
+  }
   if (water_in) {
     for (int b = 0; b < nb; ++b) {
       int r0, r1; band_rows(b, &r0, &r1);
-      if (r1 > r0)
-        TWS_CUDA(s, cudaMemcpy2DAsync(s->planes.d[src] + off + (size_t)r0 * g.pitch, dp, (const uint8_t*)water_in + (size_t)r0 * hp, hp, hp,
-                                      (size_t)(r1 - r0), cudaMemcpyHostToDevice, s->st_h2d));
+      TWS_CUDA(s, upload_rows(std::max(r0, e_top), std::min(r1, g.rows - e_bot)));
       TWS_CUDA(s, cudaEventRecord(s->band_ev[2 * b], s->st_h2d));
     }
   }
   for (int b = 0; b < nb; ++b) {
     int r0, r1; band_rows(b, &r0, &r1);
     if (water_in) TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->band_ev[2 * std::min(b + 1, nb - 1)], 0));
+    if (strip) {
+      // the first / last band reads the halo rows: the neighbour's push (this step's upload, or the previous step's
+      // output rows) must have landed
+      const int wu = (b == 0 && g.has_up) ? 1 : 0, wd = (b == nb - 1 && g.has_down) ? 1 : 0;
+      if (wu || wd) { TWS_CUDA(s, launch_wait_flags(s->ctrl, wu, wd, s->epoch, s->st_main)); s->launches += 1; }
+    }
     const int u0 = b * band_units, u1 = std::min(units, (b + 1) * band_units);
     if (stream_be) TWS_CUDA(s, launch_stream(1, g, s->planes, s->tma_stream[src], src, s->consts, r0, r1, s->st_main, stream_impl(s), s->ctrl->sched_main));
     else TWS_CUDA(s, launch_fused(1, g, s->planes, s->tma[1][src], src, s->consts, u0, u1, s->st_main));
@@ -800,6 +879,14 @@ tws_status tws_step_host(tws_sim* s, const float* water_in, float* water_out, vo
     }
   }
   s->cur = dst;
+  TWS_CUDA(s, cudaEventRecord(s->ev_main, s->st_main));
+  if (strip) {
+    // the new edge rows (depth + flux) into the neighbours' halo rows, then the flag: what tws_step's launches do themselves
+    TWS_CUDA(s, cudaStreamWaitEvent(s->st_edge, s->ev_main, 0));
+    r = push_edges(s, dst, false, s->st_edge); if (r) return r;
+    r = post_and_count(s, s->st_edge); if (r) return r;
+    TWS_CUDA(s, cudaEventRecord(s->ev_edge, s->st_edge));
+  }
   TWS_CUDA(s, cudaEventRecord(s->ev_stop, s->st_main));
   s->timed = true;
   TWS_CUDA(s, cudaStreamSynchronize(s->st_h2d));
@@ -811,6 +898,10 @@ tws_status tws_advance(tws_sim* s, double frame_seconds, uint32_t* steps_done) {
   if (steps_done) *steps_done = 0;
   if (!s) return TWS_ERR_INVALID;
   if (!(frame_seconds >= 0.0) || std::isinf(frame_seconds)) return fail(s, TWS_ERR_INVALID, "tws_advance: frame time must be finite and >= 0");
+  // the reference casts the quotient straight to a 32-bit unsigned (:243), undefined beyond 2^32: refuse such a frame
+  // before the accumulator is touched instead of running with a garbage count
+  if (!((s->accumulator + frame_seconds) / s->step_length < 4294967296.0))
+    return fail(s, TWS_ERR_INVALID, "tws_advance: frame time / step length does not fit the reference's 32-bit step counter");
   s->accumulator += frame_seconds;                                                    // Terrain.cpp:242
   uint32_t n = (uint32_t)(s->accumulator / s->step_length);                           // :243
   s->accumulator -= s->step_length * n;                                               // :244
@@ -849,6 +940,22 @@ tws_status tws_boundary_outflow(tws_sim* s, double* flux_sum) {
   return TWS_OK;
 }
 
+tws_status tws_boundary_outflow_accumulated(tws_sim* s, double* volume) {
+  if (!s || !volume) return TWS_ERR_INVALID;
+  DeviceGuard guard(s->prm.device);
+  tws_status r = sync_all(s);
+  if (r) return r;
+  TWS_CUDA(s, cudaMemcpy(volume, &s->ctrl->outflow_acc, sizeof(double), cudaMemcpyDeviceToHost));
+  return TWS_OK;
+}
+
+tws_status tws_boundary_outflow_reset(tws_sim* s) {
+  if (!s) return TWS_ERR_INVALID;
+  DeviceGuard guard(s->prm.device);
+  TWS_CUDA(s, cudaMemsetAsync(&s->ctrl->outflow_acc, 0, sizeof(double), s->st_main));
+  return TWS_OK;
+}
+
 tws_status tws_sync(tws_sim* s) {
   if (!s) return TWS_ERR_INVALID;
   DeviceGuard guard(s->prm.device);
@@ -862,6 +969,27 @@ tws_status tws_elapsed_ms(tws_sim* s, float* ms) {
   TWS_CUDA(s, cudaEventSynchronize(s->ev_stop));
   TWS_CUDA(s, cudaEventElapsedTime(ms, s->ev_start, s->ev_stop));
   return TWS_OK;
+}
+
+// gl::TimerQuery semantics (TimerQuery.cpp:61-72 with wait = false; read one frame late at Scene.cpp:337-342): never blocks.
+tws_status tws_elapsed_ms_nowait(tws_sim* s, float* ms, uint64_t* batch_index) {
+  if (!s || !ms) return TWS_ERR_INVALID;
+  if (!s->timed) return fail(s, TWS_ERR_STATE, "no step batch has been timed yet");
+  DeviceGuard guard(s->prm.device);
+  // newest first: the most recent batch if the GPU is already through with it, else the one before
+  for (uint64_t back = 0; back < 2 && back < s->batches_timed; ++back) {
+    const uint64_t idx = s->batches_timed - 1 - back;
+    const int p = (int)(idx & 1u);
+    const cudaError_t q = cudaEventQuery(s->ev_pair[p][1]);
+    if (q == cudaSuccess) {
+      TWS_CUDA(s, cudaEventElapsedTime(ms, s->ev_pair[p][0], s->ev_pair[p][1]));
+      if (batch_index) *batch_index = idx;
+      return TWS_OK;
+    }
+    if (q != cudaErrorNotReady) return cuda_fail(s, q, "cudaEventQuery");
+    (void)cudaGetLastError();
+  }
+  return fail(s, TWS_ERR_STATE, "no timed batch has finished on the GPU yet");
 }
 
 uint64_t tws_kernel_launches(const tws_sim* s) { return s ? s->launches : 0; }
@@ -932,7 +1060,7 @@ static tws_status open_peer(tws_sim* s, const tws_halo_handle* h, Peer* p, bool 
     base = (uint8_t*)ptr;
     p->ipc = true;
   }
-  p->present = true; p->slab = base; p->rows = rows;
+  p->present = true; p->slab = base; p->rows = rows; p->device = h->device;
   layout_planes(base, s->geom.pitch, rows, &p->planes, nullptr, nullptr);
   p->ctrl = (Control*)base;
   return TWS_OK;
@@ -947,6 +1075,9 @@ tws_status tws_halo_connect(tws_sim* s, const tws_halo_handle* up, const tws_hal
   if (r) return r;
   r = open_peer(s, down, &s->down, false);
   if (r) return r;
+  // (re)connecting is the recovery path after an exchange time-out: the sticky error flag starts clean
+  TWS_CUDA(s, cudaMemsetAsync(&s->ctrl->error, 0, sizeof(uint32_t), s->st_main));
+  TWS_CUDA(s, cudaStreamSynchronize(s->st_main));
   s->connected = true;
   return TWS_OK;
 }
@@ -1006,14 +1137,24 @@ tws_status publish_level0(tws_sim* s) {
   s->published_levels = 1;
   return TWS_OK;
 }
-// levels 1.. of the published TerrainInfo (Terrain.cpp:272-276); whole grids only: a strip cannot filter across its seam
+// Levels a strip can filter from its own rows alone: level l needs the strip cut on a multiple of 2^l rows (then its
+// rows of level l are exactly rows [row_begin >> l, row_end >> l) of the whole grid's level l: 2x2 boxes never straddle
+// the seam and no source coordinate is clamped in y).  A whole grid has the full chain.
+int strip_mip_levels(const Geom& g) {
+  const int full = tws_mip_levels(g.W, g.Hg);
+  if (!g.has_up && !g.has_down && g.rows == g.Hg) return full;
+  int l = 0;
+  while (l + 1 < full && (g.row0 % (2 << l)) == 0 && (g.rows % (2 << l)) == 0) ++l;
+  return l + 1;
+}
+// levels 1.. of the published TerrainInfo (Terrain.cpp:272-276).  A strip publishes the levels it can filter without its
+// neighbours (strip_mip_levels; plan_strips cuts on multiples of 8 rows, so at least levels 0-3); the consumer gathers
+// the strips' level L rows and filters the few remaining small levels itself (tws.h).
 tws_status publish_chain(tws_sim* s) {
   const Geom& g = s->geom;
-  if (g.has_up || g.has_down || g.rows != g.Hg)
-    return fail(s, TWS_ERR_UNSUPPORTED, "the mip chain is built for whole grids only (publish level 0 per strip and filter on the renderer's GPU)");
   tws_status r = publish_level0(s);
   if (r) return r;
-  const int L = tws_mip_levels(g.W, g.rows);
+  const int L = strip_mip_levels(g);
   float* base = (float*)s->packed_info;
   // large levels: one launch each; from the first level of <= 16 K texels on, the whole tail in one launch
   int first_tail = L;

@@ -36,6 +36,11 @@ struct Control {
   // sched_*[2] counts the warps that have finished an edge piece of a strip launch (the last one posts the flags).
   alignas(128) uint32_t sched_main[4];
   alignas(128) uint32_t sched_edge[4];
+  // EXT mass ledger: fp64 sum of (outflow across the edge of the GLOBAL grid) x areaInv over every sub-step this sim has
+  // run, i.e. the volume that left the map through this strip's part of the edge (flowApply.comp:38-41 with the exterior
+  // reading 0).  Accumulated by the step kernels themselves (atomicAdd from the lanes that own an edge cell), so it is
+  // exact for k steps per launch, where the intermediate fluxes never reach HBM.
+  alignas(128) double outflow_acc;
 };
 
 static_assert(sizeof(Control) <= TWS_CTRL_BYTES, "the control block must fit in front of the planes");
@@ -45,6 +50,7 @@ struct StepConsts {
   float rain_step, evap_step;        // EXT, already multiplied by dt
   int   closed;                      // EXT boundary
   int   ext_sources;                 // rain_step != 0 || evap_step != 0
+  double* ledger;                    // EXT: &Control::outflow_acc, or nullptr (closed boundary: nothing can leave)
 };
 
 // Geometry handed to every kernel.

@@ -147,6 +147,15 @@ class Terrain:
         self._check(self._lib.tws_elapsed_ms(self._sim, C.byref(ms)))
         return float(ms.value)
 
+    def elapsed_ms_nowait(self):
+        """(ms, batch index) of the newest step batch the GPU has finished, or None — never blocks (gl::TimerQuery)."""
+        ms, idx = C.c_float(0), C.c_uint64(0)
+        st = self._lib.tws_elapsed_ms_nowait(self._sim, C.byref(ms), C.byref(idx))
+        if st == _abi.TWS_ERR_STATE:
+            return None
+        self._check(st)
+        return float(ms.value), int(idx.value)
+
     def kernel_launches(self) -> int:
         return int(self._lib.tws_kernel_launches(self._sim))
 
@@ -174,6 +183,16 @@ class Terrain:
         v = C.c_double(0)
         self._check(self._lib.tws_boundary_outflow(self._sim, C.byref(v)))
         return float(v.value)
+
+    def boundary_outflow_accumulated(self) -> float:
+        """Volume that has left the map through this strip's part of the edge since creation / reset (fp64, accumulated
+        inside the step kernels in every sub-step — works with k steps per launch)."""
+        v = C.c_double(0)
+        self._check(self._lib.tws_boundary_outflow_accumulated(self._sim, C.byref(v)))
+        return float(v.value)
+
+    def boundary_outflow_reset(self) -> None:
+        self._check(self._lib.tws_boundary_outflow_reset(self._sim))
 
     _SHAPES = {
         _abi.FIELD_TERRAIN: (np.float32, ()),

@@ -23,6 +23,9 @@ int main(int argc, char** argv) {
       const uint32_t n = t.PerformSimulationStep(0.05);
       t.Sync();
       std::printf("steps=%u v0=%.6f v1=%.6f ms=%.4f\n", n, v0, t.TotalVolume(), t.SimulationTimeMs());
+      float ms_nowait = -1.0f;
+      const bool have = t.SimulationTimeMsNoWait(&ms_nowait);   // gl::TimerQuery semantics: last finished batch, no wait
+      std::printf("nowait=%d ms=%.4f outflow=%.6f\n", (int)have, ms_nowait, t.BoundaryOutflowVolume());
       int32_t levels = 0;
       const void* chain = t.PublishMips(&levels);          // GenMipMaps of TerrainInfo, Terrain.cpp:272-276
       int32_t lw = 0, lh = 0; int64_t off = 0;

@@ -273,6 +273,110 @@ def test_boundary_outflow_ledger_matches_oracle(tws, oracle):
         assert abs((vol - sim.total_volume()) - lost) / vol < 1e-6
 
 
+def _oracle_outflow_per_step(oracle, t, f, v, c, n, rain=0.0, evap=0.0):
+    """n oracle steps; returns the fp64 sum over the steps of (flux pointing out of the grid) * areaInv, summed the way
+    tests/test_oracle.py::test_open_volume_change_equals_boundary_outflow does (flowApply.comp:38-41 with exterior = 0)."""
+    lost = 0.0
+    for _ in range(n):
+        oracle.flow_update(t, f, c)
+        out = (f[:, -1, 0].sum(dtype=np.float64) + f[:, 0, 1].sum(dtype=np.float64) + f[-1, :, 2].sum(dtype=np.float64) + f[0, :, 3].sum(dtype=np.float64))
+        oracle.flow_apply(t, f, v, c, rain, evap)
+        lost += float(out) * float(c[2])
+    return lost
+
+
+@pytest.mark.parametrize("name,backend,k", BACKENDS)
+@pytest.mark.parametrize("W,H", [(96, 80), (250, 190), (130, 29), (5, 3)])
+def test_boundary_outflow_accumulated_in_kernel_matches_oracle(tws, oracle, W, H, name, backend, k):
+    """The in-kernel fp64 ledger (every sub-step, k steps per launch included) against the oracle's per-step sum; the
+    state stays bit-identical, the drained volume closes the open-domain balance."""
+    h, d = dam_break(W, H, rim=False)
+    d[:, -max(1, W // 5):] = 7.0          # water at the +X edge too
+    d[: max(1, H // 6)] += 3.0            # ... and along row 0
+    c = oracle.derive_consts(float(W), W)
+    t, f, v = new_state(h, d)
+    with make_sim(tws, W, H, backend, k) as sim:
+        sim.upload(tws.FIELD_TERRAIN, h); sim.upload(tws.FIELD_WATER, d)
+        vol0 = sim.total_volume()
+        assert sim.boundary_outflow_accumulated() == 0.0
+        want = 0.0
+        for n in (1, 7, 4 * k, 26):       # batches that are and are not multiples of k
+            sim.step(n)
+            want += _oracle_outflow_per_step(oracle, t, f, v, c, n)
+            got = sim.boundary_outflow_accumulated()
+            assert got == pytest.approx(want, rel=1e-12, abs=1e-300), f"after a batch of {n}"
+        assert want > 0
+        assert_state_equal(sim, tws, t, f, v, name)
+        assert abs((vol0 - sim.total_volume()) - got) / vol0 < 1e-6          # volume lost == volume counted out
+        sim.boundary_outflow_reset()
+        assert sim.boundary_outflow_accumulated() == 0.0
+        sim.step(3)
+        assert sim.boundary_outflow_accumulated() == pytest.approx(_oracle_outflow_per_step(oracle, t, f, v, c, 3), rel=1e-12)
+    # closed boundary: nothing can leave
+    with make_sim(tws, W, H, backend, k, boundary=tws.BOUNDARY_CLOSED) as sim:
+        sim.upload(tws.FIELD_TERRAIN, h); sim.upload(tws.FIELD_WATER, d)
+        sim.step(9)
+        assert sim.boundary_outflow_accumulated() == 0.0
+
+
+@pytest.mark.parametrize("name,backend,k", [BACKENDS[1], BACKENDS[4], BACKENDS[8], BACKENDS[12]])
+def test_ledger_with_rain_and_evaporation_closes(tws, oracle, name, backend, k):
+    """SURVEY 8d config 5 in small: V(t) = V0 + rain - evaporation - boundary outflow, with the net source taken from
+    the oracle (evaporation is clamped at dry cells, so it is not rate x area) and the outflow from the in-kernel ledger."""
+    W, H = 250, 190
+    h, d = dam_break(W, H, rim=False)
+    c = oracle.derive_consts(float(W), W)
+    rain, evap = 0.6, 0.3
+    dt = float(np.float32(1.0) / np.float32(60.0))
+    rs, es = float(np.float32(dt * rain)), float(np.float32(dt * evap))
+    t, f, v = new_state(h, d)
+    with make_sim(tws, W, H, backend, k, rain_rate=rain, evaporation_rate=evap) as sim:
+        sim.upload(tws.FIELD_TERRAIN, h); sim.upload(tws.FIELD_WATER, d)
+        sim.step(60)
+        want = _oracle_outflow_per_step(oracle, t, f, v, c, 60, rs, es)
+        assert sim.boundary_outflow_accumulated() == pytest.approx(want, rel=1e-12)
+        assert_state_equal(sim, tws, t, f, v, name)
+
+
+def test_elapsed_ms_nowait_reads_the_previous_batch_without_blocking(tws):
+    """gl::TimerQuery semantics (TimerQuery.cpp:29-72, read one frame late at Scene.cpp:337-342): double-buffered event
+    pairs; the non-blocking read returns the newest FINISHED batch and never waits for the GPU."""
+    import time
+    with make_sim(tws, 4096, 4096, tws.BACKEND_BAND_TB, 4) as sim:
+        sim.CreateHeightmapFromNoiseAndResetSim()
+        assert sim.elapsed_ms_nowait() is None               # nothing timed yet
+        sim.step(4); sim.sync()
+        ms0, idx0 = sim.elapsed_ms_nowait()
+        assert idx0 == 0 and ms0 > 0 and ms0 == pytest.approx(sim.elapsed_ms(), rel=1e-6)
+        sim.step(4); sim.sync()
+        sim.step(400)                                        # ~50 ms of GPU work queued: the call below must not wait for it
+        t0 = time.perf_counter()
+        got = sim.elapsed_ms_nowait()
+        waited = time.perf_counter() - t0
+        assert got is not None
+        ms, idx = got
+        assert idx in (1, 2) and ms > 0
+        assert waited < 0.02 or idx == 2                     # it returned while batch 2 was still running (or that one was already done)
+        sim.sync()
+        ms2, idx2 = sim.elapsed_ms_nowait()
+        assert idx2 == 2 and ms2 == pytest.approx(sim.elapsed_ms(), rel=1e-6) and ms2 > 10 * ms0
+
+
+def test_advice_r1_edge_cases(tws, oracle):
+    """Brush centres beyond INT_MAX add nothing (the reference's whole-grid pass would add 0 everywhere) instead of failing;
+    a frame time whose step count overflows the reference's 32-bit counter is refused before the accumulator moves."""
+    with make_sim(tws, 64, 64, tws.BACKEND_FUSED, 1) as sim:
+        d = np.ones((64, 64), np.float32)
+        sim.upload(tws.FIELD_WATER, d)
+        for cx, cy in ((3.0e9, 10.0), (-3.0e9, 10.0), (10.0, 3.0e9), (10.0, -3.0e9), (3.0e38, -3.0e38)):
+            sim.inject_brush(cx, cy, 2.0, 32.0)
+        assert np.array_equal(sim.readback(tws.FIELD_WATER), d)
+        with pytest.raises(tws.TwsError) as e:
+            sim.PerformSimulationStep(1.0e9)
+        assert e.value.status == tws._abi.TWS_ERR_INVALID
+        assert sim.PerformSimulationStep(1.0) == 10          # the accumulator was not poisoned by the refused frame
+
+
 def test_parameter_validation_on_device(tws):
     with make_sim(tws, 64, 64, tws.BACKEND_FUSED, 1) as sim:
         for call in (lambda: sim.SetSimulationStepsPerSecond(0.0), lambda: sim.SetFlowDamping(-1.0), lambda: sim.SetFlowAcceleration(float("nan")),
