@@ -575,6 +575,7 @@ def run_b200(args):
 
 
 def main():
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")     # one hardware queue per stream (set before CUDA initialises)
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

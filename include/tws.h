@@ -57,9 +57,12 @@ typedef enum tws_backend {
   TWS_BACKEND_STREAM_TB = 4,/* fused + temporal blocking as a row-streaming pipeline: one warp
                                per grid row, rows skewed in time instead of recomputed,
                                `temporal_block` steps per HBM round trip                  */
-  TWS_BACKEND_BAND_TB = 5   /* the same skewed row streaming run in lock step: bands of rows,
+  TWS_BACKEND_BAND_TB = 5,  /* the same skewed row streaming run in lock step: bands of rows,
                                one group barrier per half-pass instead of per-row barriers,
                                dynamic piece schedule, strip exchange fused into the launch */
+  TWS_BACKEND_CHAIN_TB = 6  /* the same strips streamed through chains of `temporal_block` warps, warp s
+                               applying step s+1 to rows it holds in registers: no neighbour
+                               synchronisation inside a step, warps linked by shared-memory row rings */
 } tws_backend;
 
 typedef enum tws_boundary {
@@ -96,7 +99,7 @@ typedef struct tws_params {
   float    flow_acceleration; /* Terrain::SetFlowAcceleration,   default 10                  */
   int32_t  boundary;          /* tws_boundary                                                */
   int32_t  backend;           /* tws_backend                                                 */
-  int32_t  temporal_block;    /* steps fused per launch for FUSED_TB / STREAM_TB / BAND_TB (1..4); ignored otherwise */
+  int32_t  temporal_block;    /* steps fused per launch for FUSED_TB / STREAM_TB / BAND_TB / CHAIN_TB (1..4); ignored otherwise */
   int32_t  device;            /* CUDA device ordinal                                         */
   float    rain_rate;         /* EXTENSION: uniform depth added per second (0 = off)         */
   float    evaporation_rate;  /* EXTENSION: uniform depth removed per second (0 = off)       */
@@ -241,7 +244,9 @@ tws_status tws_device_view(tws_sim* s, tws_field field, void** device_ptr, int64
  * neighbour's memory; the neighbour's edge rows wait on that flag while its interior
  * rows are computed.  tws_halo_refresh pushes the current state (after upload / reset /
  * inject); call it on all strips, then tws_sync + a host barrier.  Strips that share
- * one device are a test configuration: their launches wait for each other on the GPU. */
+ * one device are a test configuration: their launches wait for each other on the GPU with
+ * spinning flag kernels, so every stream needs its own hardware queue — run such a process
+ * with CUDA_DEVICE_MAX_CONNECTIONS=32 (each sim owns up to four streams). */
 tws_status tws_halo_export(tws_sim* s, tws_halo_handle* out);
 tws_status tws_halo_connect(tws_sim* s, const tws_halo_handle* up, const tws_halo_handle* down);
 tws_status tws_halo_refresh(tws_sim* s);

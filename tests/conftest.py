@@ -1,5 +1,13 @@
+import os
 import sys
 from pathlib import Path
+
+# Several strip sims of ONE test process share one GPU and wait for each other with spinning flag kernels; with more
+# streams than hardware work queues (default 8) two streams can alias onto one queue and a wait kernel then blocks the very
+# push it is waiting for.  32 queues keep every stream of the test configurations on its own queue.  Must be set before
+# CUDA initialises.  (One process per GPU — the deployment — never depends on it: a wait only needs work that was
+# enqueued before it.)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import pytest
 
