@@ -57,12 +57,9 @@ typedef enum tws_backend {
   TWS_BACKEND_STREAM_TB = 4,/* fused + temporal blocking as a row-streaming pipeline: one warp
                                per grid row, rows skewed in time instead of recomputed,
                                `temporal_block` steps per HBM round trip                  */
-  TWS_BACKEND_BAND_TB = 5,  /* the same skewed row streaming run in lock step: bands of rows,
+  TWS_BACKEND_BAND_TB = 5   /* the same skewed row streaming run in lock step: bands of rows,
                                one group barrier per half-pass instead of per-row barriers,
                                dynamic piece schedule, strip exchange fused into the launch */
-  TWS_BACKEND_CHAIN_TB = 6  /* the same strips streamed through chains of `temporal_block` warps, warp s
-                               applying step s+1 to rows it holds in registers: no neighbour
-                               synchronisation inside a step, warps linked by shared-memory row rings */
 } tws_backend;
 
 typedef enum tws_boundary {
@@ -99,7 +96,7 @@ typedef struct tws_params {
   float    flow_acceleration; /* Terrain::SetFlowAcceleration,   default 10                  */
   int32_t  boundary;          /* tws_boundary                                                */
   int32_t  backend;           /* tws_backend                                                 */
-  int32_t  temporal_block;    /* steps fused per launch for FUSED_TB / STREAM_TB / BAND_TB / CHAIN_TB (1..4); ignored otherwise */
+  int32_t  temporal_block;    /* steps fused per launch for FUSED_TB / STREAM_TB / BAND_TB (1..4); ignored otherwise */
   int32_t  device;            /* CUDA device ordinal                                         */
   float    rain_rate;         /* EXTENSION: uniform depth added per second (0 = off)         */
   float    evaporation_rate;  /* EXTENSION: uniform depth removed per second (0 = off)       */

@@ -550,7 +550,6 @@ cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& t
                           cudaStream_t st, int impl, uint32_t* sched, int cta_budget) {
   const bool ext = c.ext_sources != 0;
   if (impl == 1) return launch_band(K, g, p, tma, src, c, lr0, lr1, st, sched, cta_budget);
-  if (impl == 2) return launch_chain(K, g, p, tma, src, c, lr0, lr1, st, sched);
   switch (K) {
     case 1: return ext ? launch_stream_k<1, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<1, false>(g, p, tma, src, c, lr0, lr1, st);
     case 2: return ext ? launch_stream_k<2, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<2, false>(g, p, tma, src, c, lr0, lr1, st);

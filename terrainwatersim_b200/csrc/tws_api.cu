@@ -129,8 +129,8 @@ int pitch_for(int width) { return (int)align_up((size_t)width, 64); }
 
 // Terrain.cpp:175-198 — see tws_step_constants in tws.h.
 void drop_graphs(tws_sim* s);
-inline bool is_stream_backend(int b) { return b == TWS_BACKEND_STREAM_TB || b == TWS_BACKEND_BAND_TB || b == TWS_BACKEND_CHAIN_TB; }
-inline int stream_impl(const tws_sim* s) { return s->prm.backend == TWS_BACKEND_BAND_TB ? 1 : (s->prm.backend == TWS_BACKEND_CHAIN_TB ? 2 : 0); }
+inline bool is_stream_backend(int b) { return b == TWS_BACKEND_STREAM_TB || b == TWS_BACKEND_BAND_TB; }
+inline int stream_impl(const tws_sim* s) { return s->prm.backend == TWS_BACKEND_BAND_TB ? 1 : 0; }
 void derive_constants(tws_sim* s) {
   drop_graphs(s);                                       // captured batches bake the constants in
   const tws_params& p = s->prm;
@@ -497,7 +497,7 @@ tws_status tws_create(const tws_params* p, tws_sim** out) {
   if (bad_float(p->flow_acceleration) || p->flow_acceleration < 0.0f) return fail(nullptr, TWS_ERR_INVALID, "tws_create: flow_acceleration must be >= 0");
   if (bad_float(p->rain_rate) || bad_float(p->evaporation_rate) || p->rain_rate < 0.0f || p->evaporation_rate < 0.0f)
     return fail(nullptr, TWS_ERR_INVALID, "tws_create: rain/evaporation must be >= 0");
-  if (p->backend < TWS_BACKEND_AUTO || p->backend > TWS_BACKEND_CHAIN_TB) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown backend");
+  if (p->backend < TWS_BACKEND_AUTO || p->backend > TWS_BACKEND_BAND_TB) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown backend");
   if (p->boundary != TWS_BOUNDARY_REFERENCE_OPEN && p->boundary != TWS_BOUNDARY_CLOSED) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown boundary");
   if ((p->backend == TWS_BACKEND_FUSED_TB || is_stream_backend(p->backend)) && (p->temporal_block < 1 || p->temporal_block > TWS_MAX_TB))
     return fail(nullptr, TWS_ERR_INVALID, "tws_create: temporal_block must be 1..4");

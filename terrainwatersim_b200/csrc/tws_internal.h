@@ -110,7 +110,7 @@ cudaError_t build_tma_boxes(const Geom& g, const Planes& p, int side, int box_x,
                             int l2_promotion);   // 0 none, 1 128 B, 2 256 B
 cudaError_t build_tma_rows(const Geom& g, const Planes& p, int side, int box_x, TmaSet* out, std::string* err, int l2_promotion);
 cudaError_t stream_build_tma(const Geom& g, const Planes& p, int side, TmaSet* out, std::string* err);
-// impl 0: ring kernel (one warp per row, per-row barriers); impl 1: band kernel (CTA-synchronous skewed bands); impl 2: chain kernel.
+// impl 0: ring kernel (one warp per row, per-row barriers); impl 1: band kernel (CTA-synchronous skewed bands).
 // sched: the Control counter pair of the launching stream (band kernel; nullptr = static round-robin pieces).
 // cta_budget (band kernel): 0 = one CTA per SM, n > 0 = at most n CTAs, n < 0 = leave -n SMs free.
 cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c,
@@ -121,10 +121,6 @@ cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& t
 cudaError_t launch_band(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c,
                         int lr0, int lr1, cudaStream_t st, uint32_t* sched, int cta_budget, const BandEdge* edge = nullptr,
                         int e_top = 0, int e_bot = 0);
-// Chain kernel (chain_kernels.cu): the same strips streamed through chains of K warps, rows held in registers, no neighbour
-// synchronisation inside a step; same row descriptors as the ring kernel.
-cudaError_t launch_chain(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c,
-                         int lr0, int lr1, cudaStream_t st, uint32_t* sched);
 int stream_strip_width();
 cudaError_t launch_unfused_update(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st);
 cudaError_t launch_unfused_apply(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st);

@@ -218,7 +218,7 @@ def test_strip_ledgers_add_up_to_the_whole_grid_ledger(tws, oracle, k, backend):
             s.close()
 
 
-@pytest.mark.parametrize("nstrips,backend,k,rows_per_strip", [(2, 5, 4, 1100), (3, 5, 1, 24), (3, 2, 1, 200), (2, 4, 3, 8), (3, 3, 2, 40), (2, 5, 1, 9), (2, 2, 1, 300), (2, 6, 4, 700)])
+@pytest.mark.parametrize("nstrips,backend,k,rows_per_strip", [(2, 5, 4, 1100), (3, 5, 1, 24), (3, 2, 1, 200), (2, 4, 3, 8), (3, 3, 2, 40), (2, 5, 1, 9), (2, 2, 1, 300)])
 @pytest.mark.parametrize("spread", [False, True], ids=["one-gpu", "multi-gpu"])
 def test_step_host_on_strips_is_pipelined_and_matches_the_oracle(tws, oracle_omp, nstrips, backend, k, rows_per_strip, spread):
     """tws_step_host on strips (the e2e leg of bench.py at N > 1): every step the host uploads a NEW water layer (the edge
