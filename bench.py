@@ -380,17 +380,19 @@ def run_b200(args):
     launches = int(sum_over_ranks(float(launches_local)))
     value = cells_global * args.steps / (ms * 1e-3) / 1e9
     clock_note = None
-    if len(sampler.inside()) < 5 and sampler.ok:
+    if ms < 40.0:
         # the timed region was shorter than a handful of NVML samples (e.g. --steps 20 = 4 ms): keep the SAME kernel running,
-        # untimed, until the sampler has seen the GPU under this load
+        # untimed, for ~60 ms so that the sampler sees the GPU under this load.  The count derives from `ms` (max over ranks),
+        # so every rank runs the same number of steps — strips step in lock step with their neighbours.
+        extra = int(min(4000, max(4 * k, 60.0 / max(ms / args.steps, 1e-3))))
+        extra = (extra + k - 1) // k * k
+        barrier()
         t0 = time.perf_counter()
-        extra = 0
-        while len(sampler.inside()) + len([x for x in sampler.samples if x[0] >= t0]) < 8 and time.perf_counter() - t0 < 2.0:
-            sim.step(4 * k)
-            sim.sync()
-            extra += 4 * k
+        sim.step(extra)
+        sim.sync()
         sampler.mark(t0, time.perf_counter())
-        clock_note = f"timed region ({ms:.1f} ms) shorter than the NVML sampling period x 5: samples include {extra} further untimed steps of the same kernel run right after it"
+        barrier()
+        clock_note = f"timed region ({ms:.1f} ms) shorter than a handful of NVML samples: clocks sampled over it and over {extra} further untimed steps of the same kernel run right after it"
     clocks = sampler.summary(clock_note)
 
     # ---- roofline of the dominant kernel (the step kernel; all launches in the region are it) -------

@@ -854,7 +854,11 @@ tws_status tws_step_host(tws_sim* s, const float* water_in, float* water_out, vo
       TWS_CUDA(s, cudaEventRecord(s->band_ev[2 * b], s->st_h2d));
     }
   }
-  for (int b = 0; b < nb; ++b) {
+  // Strips compute the bands that read a halo LAST (1, 2, ..., nb-2, then 0 and nb-1): by then the neighbours' pushes
+  // have long landed, so a rank that entered the call a little later than its neighbour stalls nobody's pipeline.
+  for (int ord = 0; ord < nb; ++ord) {
+    int b = ord;
+    if (strip && nb >= 3) b = ord < nb - 2 ? ord + 1 : (ord == nb - 2 ? 0 : nb - 1);
     int r0, r1; band_rows(b, &r0, &r1);
     if (water_in) TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->band_ev[2 * std::min(b + 1, nb - 1)], 0));
     if (strip) {
