@@ -134,6 +134,54 @@ __global__ void pack_info_kernel(Geom g, float* h, float* d, float4* aos, int lr
   }
 }
 
+// The renderer hand-off in ONE pass over the planar state (Terrain.cpp:272-276,288,323-330): TerrainInfo level 0 (r = terrain,
+// g = b = 0.3, a = water), its mip level 1 (the 2x2 box of mip_level_kernel below, same operation order) and the flow map.
+// One thread per 2x2 block of cells.  Replaces pack + flow-map copy + first mip launch and the re-read of the 16 B texels
+// the first mip level would need; every frame of the reference pays for this hand-off.
+__global__ void __launch_bounds__(256) publish_fused_kernel(Geom g, const float* __restrict__ h, const float* __restrict__ d,
+                                                            const uint32_t* __restrict__ v, float4* __restrict__ l0, float4* __restrict__ l1,
+                                                            uint32_t* __restrict__ flow, int W, int H, int w1, int h1) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  if (2 * X >= W) return;
+  for (int Y = blockIdx.y; 2 * Y < H; Y += gridDim.y) {
+    const int x0 = 2 * X, x1 = min(2 * X + 1, W - 1), y0 = 2 * Y, y1 = min(2 * Y + 1, H - 1);
+    const long long o00 = (long long)y0 * g.pitch + x0, o01 = (long long)y0 * g.pitch + x1;
+    const long long o10 = (long long)y1 * g.pitch + x0, o11 = (long long)y1 * g.pitch + x1;
+    const float4 a = make_float4(h[o00], 0.3f, 0.3f, d[o00]), b = make_float4(h[o01], 0.3f, 0.3f, d[o01]);
+    const float4 c = make_float4(h[o10], 0.3f, 0.3f, d[o10]), e = make_float4(h[o11], 0.3f, 0.3f, d[o11]);
+    l0[(long long)y0 * W + x0] = a;
+    if (x1 != x0) l0[(long long)y0 * W + x1] = b;
+    if (y1 != y0) {
+      l0[(long long)y1 * W + x0] = c;
+      if (x1 != x0) l0[(long long)y1 * W + x1] = e;
+    }
+    if (flow != nullptr) {
+      flow[(long long)y0 * W + x0] = v[o00];
+      if (x1 != x0) flow[(long long)y0 * W + x1] = v[o01];
+      if (y1 != y0) {
+        flow[(long long)y1 * W + x0] = v[o10];
+        if (x1 != x0) flow[(long long)y1 * W + x1] = v[o11];
+      }
+    }
+    if (l1 != nullptr && X < w1 && Y < h1) {
+      float4 o;
+      o.x = __fmul_rn(__fadd_rn(__fadd_rn(a.x, b.x), __fadd_rn(c.x, e.x)), 0.25f);
+      o.y = __fmul_rn(__fadd_rn(__fadd_rn(a.y, b.y), __fadd_rn(c.y, e.y)), 0.25f);
+      o.z = __fmul_rn(__fadd_rn(__fadd_rn(a.z, b.z), __fadd_rn(c.z, e.z)), 0.25f);
+      o.w = __fmul_rn(__fadd_rn(__fadd_rn(a.w, b.w), __fadd_rn(c.w, e.w)), 0.25f);
+      l1[(long long)Y * w1 + X] = o;
+    }
+  }
+}
+cudaError_t launch_publish_fused(const Geom& g, const Planes& p, int side, float* level0, float* level1, uint32_t* flow, cudaStream_t st) {
+  const size_t off = (size_t)TWS_HALO_ROWS * g.pitch;
+  const int W = g.W, H = g.rows, bx = (W + 1) / 2, by = (H + 1) / 2;
+  const int w1 = W > 1 ? W >> 1 : 1, h1 = H > 1 ? H >> 1 : 1;
+  dim3 block(128), grid((bx + 127) / 128, by < 2048 ? by : 2048);
+  publish_fused_kernel<<<grid, block, 0, st>>>(g, p.h + off, p.d[side] + off, p.v + off, (float4*)level0, (float4*)level1, flow, W, H, w1, h1);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_pack_flux(const Geom& g, const Planes& p, int side, float* aos, int lr0, int nrows, bool to_aos, cudaStream_t st) {
   const size_t off = (size_t)TWS_HALO_ROWS * g.pitch;
   dim3 block(256), grid((g.W + 255) / 256, nrows < 1024 ? nrows : 1024);

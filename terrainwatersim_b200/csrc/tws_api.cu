@@ -1127,18 +1127,18 @@ size_t mip_chain_texels(int w, int h) {
   for (int l = 0, L = tws_mip_levels(w, h); l < L; ++l) n += (size_t)std::max(1, w >> l) * std::max(1, h >> l);
   return n;
 }
-// level 0 of TerrainInfo (and the flow map) into the publish buffers; the info buffer has room for the whole chain
-tws_status publish_level0(tws_sim* s) {
+// level 0 of TerrainInfo, the flow map and — with_level1 — mip level 1 into the publish buffers, in one launch; the info
+// buffer has room for the whole chain
+tws_status publish_level0(tws_sim* s, bool with_level1) {
   const Geom& g = s->geom;
   const size_t cells = (size_t)g.W * g.rows;
   if (!s->packed_info) TWS_CUDA(s, cudaMalloc(&s->packed_info, mip_chain_texels(g.W, g.rows) * 16));
   if (!s->packed_flow) TWS_CUDA(s, cudaMalloc(&s->packed_flow, cells * 4));
   if (g.has_up || g.has_down) TWS_CUDA(s, cudaStreamWaitEvent(s->st_main, s->ev_edge, 0));
-  TWS_CUDA(s, launch_pack_info(g, s->planes, s->cur, (float*)s->packed_info, 0, g.rows, true, s->st_main));
+  float* level1 = with_level1 ? (float*)s->packed_info + cells * 4 : nullptr;          // level 1 follows level 0
+  TWS_CUDA(s, launch_publish_fused(g, s->planes, s->cur, (float*)s->packed_info, level1, (uint32_t*)s->packed_flow, s->st_main));
   s->launches += 1;
-  TWS_CUDA(s, cudaMemcpy2DAsync(s->packed_flow, (size_t)g.W * 4, s->planes.v + (size_t)TWS_HALO_ROWS * g.pitch, (size_t)g.pitch * 4,
-                                (size_t)g.W * 4, g.rows, cudaMemcpyDeviceToDevice, s->st_main));
-  s->published_levels = 1;
+  s->published_levels = with_level1 ? 2 : 1;
   return TWS_OK;
 }
 // Levels a strip can filter from its own rows alone: level l needs the strip cut on a multiple of 2^l rows (then its
@@ -1156,13 +1156,14 @@ int strip_mip_levels(const Geom& g) {
 // the strips' level L rows and filters the few remaining small levels itself (tws.h).
 tws_status publish_chain(tws_sim* s) {
   const Geom& g = s->geom;
-  tws_status r = publish_level0(s);
-  if (r) return r;
   const int L = strip_mip_levels(g);
+  tws_status r = publish_level0(s, L > 1);
+  if (r) return r;
   float* base = (float*)s->packed_info;
-  // large levels: one launch each; from the first level of <= 16 K texels on, the whole tail in one launch
+  // level 1 came with level 0; further large levels: one launch each; from the first level of <= 16 K texels on, the whole
+  // tail in one launch
   int first_tail = L;
-  for (int l = 1; l < L; ++l) {
+  for (int l = 2; l < L; ++l) {
     int32_t sw, sh, dw, dh; int64_t so, d_o;
     tws_mip_level_info(g.W, g.rows, l - 1, &sw, &sh, &so);
     tws_mip_level_info(g.W, g.rows, l, &dw, &dh, &d_o);
@@ -1182,7 +1183,7 @@ tws_status publish_chain(tws_sim* s) {
 tws_status tws_publish_packed(tws_sim* s, void** info, void** flow) {
   if (!s || !info || !flow) return TWS_ERR_INVALID;
   DeviceGuard guard(s->prm.device);
-  tws_status r = publish_level0(s);
+  tws_status r = publish_level0(s, false);
   if (r) return r;
   *info = s->packed_info; *flow = s->packed_flow;
   return TWS_OK;

@@ -131,6 +131,8 @@ cudaError_t launch_scene(const Geom& g, const Planes& p, int side, const float* 
                          float persistence, int tile_h, cudaStream_t st);
 cudaError_t launch_pack_flux(const Geom& g, const Planes& p, int side, float* aos, int lr0, int nrows, bool to_aos, cudaStream_t st);
 cudaError_t launch_pack_info(const Geom& g, const Planes& p, int side, float* aos, int lr0, int nrows, bool to_aos, cudaStream_t st);
+// TerrainInfo level 0 + (level1 != nullptr) its mip level 1 + (flow != nullptr) the flow map, in one pass over the planar state
+cudaError_t launch_publish_fused(const Geom& g, const Planes& p, int side, float* level0, float* level1, uint32_t* flow, cudaStream_t st);
 // one level of the RGBA32F mip chain (2x2 box, see aux_kernels.cu): dst (dw x dh texels) <- src (sw x sh texels)
 cudaError_t launch_mip_level(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t st);
 // levels [first, last) of the chain at `base` (level L follows level L-1) in one single-CTA launch: the small tail
