@@ -206,6 +206,14 @@ tws_status tws_boundary_outflow(tws_sim* s, double* flux_sum);
  * config 5 closes the ledger V0 + sources - outflow with it.  The sum order of the atomics is not fixed: equal to the
  * oracle's per-step fp64 sum to ~1e-15 relative, not bitwise.  tws_boundary_outflow_accumulated synchronises. */
 tws_status tws_boundary_outflow_accumulated(tws_sim* s, double* volume);
+/* The other side of the ledger: the volume rain and evaporation REALLY changed since the same point in time — the fp64 sum,
+ * over every cell of the sim's own rows and every sub-step, of (depth after the source terms - depth before them) as the
+ * fp32 arithmetic produced it.  This is not rain_rate x time x area: d + rain_step - evap_step rounds the same way for every
+ * cell of a binade, and evaporation is clamped at dry cells; over 10 000 steps the difference reaches 1e-4 of the volume.
+ * total_volume(t) == total_volume(0) + tws_source_accumulated - tws_boundary_outflow_accumulated up to the (unbiased) fp32
+ * rounding of the flux updates.  0 while rain and evaporation are off.  Synchronises. */
+tws_status tws_source_accumulated(tws_sim* s, double* volume);
+/* zeroes both accumulators */
 tws_status tws_boundary_outflow_reset(tws_sim* s);
 
 /* Device-side timing of the most recent tws_step/tws_advance batch (CUDA events on the

@@ -101,6 +101,7 @@ SYMBOLS = {
     "tws_sync": (C.c_int, [_SIM]),
     "tws_boundary_outflow": (C.c_int, [_SIM, C.POINTER(C.c_double)]),
     "tws_boundary_outflow_accumulated": (C.c_int, [_SIM, C.POINTER(C.c_double)]),
+    "tws_source_accumulated": (C.c_int, [_SIM, C.POINTER(C.c_double)]),
     "tws_boundary_outflow_reset": (C.c_int, [_SIM]),
     "tws_elapsed_ms": (C.c_int, [_SIM, C.POINTER(C.c_float)]),
     "tws_elapsed_ms_nowait": (C.c_int, [_SIM, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),

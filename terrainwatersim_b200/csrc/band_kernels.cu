@@ -281,14 +281,8 @@ __device__ __forceinline__ void band_flux(GroupSync& sy, const uint32_t (&up)[R]
 // flowApply.comp:38-46 with the source/sink extension compiled in or out.
 template <bool EXT>
 __device__ __forceinline__ float band_apply_cell(float depth, float fx, float fy, float fz, float fw, float iX1, float iX0, float iY1,
-                                                 float iY0, const StepConsts& c, float& vx, float& vy) {
-  const float in = __fadd_rn(__fadd_rn(__fadd_rn(iX1, iX0), iY1), iY0);              // :38
-  const float out = __fadd_rn(__fadd_rn(__fadd_rn(fx, fy), fz), fw);                 // :39
-  float nd = max0(__fadd_rn(depth, __fmul_rn(__fsub_rn(in, out), c.area_inv)));      // :41
-  if (EXT) nd = max0(__fsub_rn(__fadd_rn(nd, c.rain_step), c.evap_step));            // EXT (same expression as apply_cell)
-  vx = __fsub_rn(__fsub_rn(iX1, fx), __fsub_rn(iX0, fy));                            // :45
-  vy = __fsub_rn(__fsub_rn(iY1, fz), __fsub_rn(iY0, fw));                            // :46
-  return nd;
+                                                 float iY0, const StepConsts& c, float& vx, float& vy, float& ds) {
+  return apply_cell_src(depth, fx, fy, fz, fw, iX1, iX0, iY1, iY0, c, EXT, vx, vy, ds);
 }
 
 // flowApply.comp:32-52 for the lane's 4 cells of each of its R rows.  Reads the neighbour rows' +-Y
@@ -299,7 +293,8 @@ template <int R, int SXW, bool EDGE, bool LAST, bool EXT>
 __device__ __forceinline__ void band_depth(GroupSync& sy, const uint32_t (&up)[R], const uint32_t (&dn)[R], const uint32_t (&me)[R],
                                            const float4 (&h)[R], float4 (&d)[R], const float4 (&fx)[R], const float4 (&fy)[R],
                                            const float4 (&fz)[R], const float4 (&fw)[R], const BandRow (&rc)[R], const int gx,
-                                           const bool st_col, const FusedOut& out, const Geom& g, const StepConsts& c, const BandEdge& edge) {
+                                           const bool st_col, const FusedOut& out, const Geom& g, const StepConsts& c, const BandEdge& edge,
+                                           double& src_acc) {
   float4 iy1[R], iy0[R];
   float l[R], r[R];
 #pragma unroll
@@ -346,7 +341,11 @@ __device__ __forceinline__ void band_depth(GroupSync& sy, const uint32_t (&up)[R
         float e0, e1, e2, e3;
         upk(sub2(add2(lo2(nd[q]), RAIN), EVAP), e0, e1);
         upk(sub2(add2(hi2(nd[q]), RAIN), EVAP), e2, e3);
+        const float4 pre = nd[q];
         nd[q] = make_float4(max0(e0), max0(e1), max0(e2), max0(e3));
+        if (rc[q].store && st_col)                       // ledger of the sources: what they changed, owner lanes, every sub-step
+          src_acc += ((double)__fsub_rn(nd[q].x, pre.x) + (double)__fsub_rn(nd[q].y, pre.y)) +
+                     ((double)__fsub_rn(nd[q].z, pre.z) + (double)__fsub_rn(nd[q].w, pre.w));
       }
       if (!LAST) {
         d[q] = nd[q];
@@ -383,11 +382,12 @@ __device__ __forceinline__ void band_depth(GroupSync& sy, const uint32_t (&up)[R
     for (int i = 0; i < 4; ++i) {
       const float iX1 = (i < 3) ? comp(fy[q], i + 1) : r[q];
       const float iX0 = (i > 0) ? comp(fx[q], i - 1) : l[q];
-      float vx, vy;
+      float vx, vy, ds;
       nds[q][i] = band_apply_cell<EXT>(comp(d[q], i), comp(fx[q], i), comp(fy[q], i), comp(fz[q], i), comp(fw[q], i), iX1, iX0,
-                                       comp(iy1[q], i), comp(iy0[q], i), c, vx, vy);
+                                       comp(iy1[q], i), comp(iy0[q], i), c, vx, vy, ds);
       nvs[q][i] = LAST ? pack_half2(vx, vy) : 0u;
-      if (EDGE && !(rc[q].row_in && (unsigned)(gx + i) < (unsigned)g.W)) { nds[q][i] = 0.f; nvs[q][i] = 0u; }
+      if (EDGE && !(rc[q].row_in && (unsigned)(gx + i) < (unsigned)g.W)) { nds[q][i] = 0.f; nvs[q][i] = 0u; ds = 0.f; }
+      if (EXT && rc[q].store && st_col) src_acc += (double)ds;
     }
     if (!LAST) {
       d[q] = make_float4(nds[q][0], nds[q][1], nds[q][2], nds[q][3]);
@@ -446,6 +446,7 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
   const uint32_t xch = smem_u32(gsm + BR * LAND + lane * 4);
   const int pw = (NW - 1 - warp) < HP ? (NW - 1 - warp) : HP;     // half-passes the last row gets inside its own band
   const bool carrier = pw < HP;
+  double src_acc = 0.0;                                   // EXT ledger of the sources: per-thread partial sum, flushed at the end
   // the half-pass before which a carrier switches to the row it parked one band ago (0: never).  Pinned in a register:
   // left to the compiler it is re-derived from the warp index (8 instructions) in front of every half-pass
   const uint32_t swap_at = keep_u32(carrier ? (uint32_t)(pw + 1) : 0u);
@@ -606,15 +607,15 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
         if (plain) band_flux<R, SXW, false, false>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
         else band_flux<R, SXW, true, false>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
         if (2 * lv == swap_at) swap_rows(j);
-        if (plain) band_depth<R, SXW, false, false, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
-        else band_depth<R, SXW, true, false, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
+        if (plain) band_depth<R, SXW, false, false, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge, src_acc);
+        else band_depth<R, SXW, true, false, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge, src_acc);
       }
       if (HP - 1 == swap_at) swap_rows(j);
       if (plain) band_flux<R, SXW, false, true>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
       else band_flux<R, SXW, true, true>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
       if (HP == swap_at) swap_rows(j);
-      if (plain) band_depth<R, SXW, false, true, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
-      else band_depth<R, SXW, true, true, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge);
+      if (plain) band_depth<R, SXW, false, true, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge, src_acc);
+      else band_depth<R, SXW, true, true, EXT>(sy, x_up, x_dn, x_me, h, d, fx, fy, fz, fw, rc, gx, st_col, out, g, c, edge, src_acc);
     }
     if (edge_piece) {
       // every lane's stores into the neighbours' halos are visible system-wide before this warp counts itself done;
@@ -632,6 +633,7 @@ __global__ void __launch_bounds__(C::NT, 1) band_step_kernel(const __grid_consta
     piece = sched ? *(volatile int*)&next_piece[grp][pp] : piece + nvcta;
     pp ^= 1;
   }
+  if (EXT) ledger_src_flush(c.ledger_src, src_acc);
   // the last group to leave re-arms the counters for the next launch on this stream (every group that had a
   // piece has by then seen its final, failing fetch, so no atomic on the counter is still in flight)
   if (sched && vcta < sch.npieces && warp == 0 && lane == 0) {

@@ -57,16 +57,36 @@ __device__ __forceinline__ void flux_cell(float Hc, float Hxp, float Hxm, float 
   }
 }
 
-// flowApply.comp:38-46.  Returns the new depth; vx, vy the flow vector.
-__device__ __forceinline__ float apply_cell(float depth, float fx, float fy, float fz, float fw, float iX1, float iX0,
-                                            float iY1, float iY0, const StepConsts& c, float& vx, float& vy) {
+// flowApply.comp:38-46.  Returns the new depth; vx, vy the flow vector; ds (EXT ledger) what rain / evaporation really
+// changed in fp32: depth after the source terms minus depth before them (exact: the two are within a factor of two of each
+// other, or the difference is below half an ulp of either and irrelevant), 0 without sources.
+__device__ __forceinline__ float apply_cell_src(float depth, float fx, float fy, float fz, float fw, float iX1, float iX0,
+                                                float iY1, float iY0, const StepConsts& c, const bool ext, float& vx, float& vy, float& ds) {
   const float in = __fadd_rn(__fadd_rn(__fadd_rn(iX1, iX0), iY1), iY0);              // :38
   const float out = __fadd_rn(__fadd_rn(__fadd_rn(fx, fy), fz), fw);                 // :39
   float nd = max0(__fadd_rn(depth, __fmul_rn(__fsub_rn(in, out), c.area_inv)));      // :41
-  if (c.ext_sources) nd = max0(__fsub_rn(__fadd_rn(nd, c.rain_step), c.evap_step));  // EXT
+  ds = 0.0f;
+  if (ext) {                                                                         // EXT
+    const float pre = nd;
+    nd = max0(__fsub_rn(__fadd_rn(nd, c.rain_step), c.evap_step));
+    ds = __fsub_rn(nd, pre);
+  }
   vx = __fsub_rn(__fsub_rn(iX1, fx), __fsub_rn(iX0, fy));                            // :45
   vy = __fsub_rn(__fsub_rn(iY1, fz), __fsub_rn(iY0, fw));                            // :46
   return nd;
+}
+__device__ __forceinline__ float apply_cell(float depth, float fx, float fy, float fz, float fw, float iX1, float iX0,
+                                            float iY1, float iY0, const StepConsts& c, float& vx, float& vy) {
+  float ds;
+  return apply_cell_src(depth, fx, fy, fz, fw, iX1, iX0, iY1, iY0, c, c.ext_sources != 0, vx, vy, ds);
+}
+
+// EXT ledger of the sources (Control::source_acc): per-thread fp64 partial sums of the source deltas of OWNED cells,
+// flushed by whole warps (shuffle reduction, one atomicAdd per warp).
+__device__ __forceinline__ void ledger_src_flush(double* dst, double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (dst != nullptr && (threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(dst, v);
 }
 
 // EXT mass ledger (Control::outflow_acc).  Called by the ONE lane that owns the four cells (gx0..gx0+3, gy) as output
@@ -185,7 +205,7 @@ __device__ __forceinline__ void flux_raw4(const float4& HC, const float4& HU, co
 template <bool VEL>
 __device__ __forceinline__ void apply4(const float4& d, const float4& fx, const float4& fy, const float4& fz, const float4& fw, float l,
                                        float r, const float4& iy1, const float4& iy0, const StepConsts& c, const bool ext, float4& nd,
-                                       uint4& nv) {
+                                       uint4& nv, float4* ds = nullptr /* EXT ledger: source delta per cell */) {
   // iX1 = F(x+1,y).y (:32), iX0 = F(x-1,y).x (:33): neighbours inside the group are misaligned pairs -> scalar
   const float a0 = __fadd_rn(fy.y, l), a1 = __fadd_rn(fy.z, fx.x), a2 = __fadd_rn(fy.w, fx.y), a3 = __fadd_rn(r, fx.z);
   const f2 inlo = add2(add2(pk(a0, a1), lo2(iy1)), lo2(iy0));                        // :38
@@ -202,7 +222,11 @@ __device__ __forceinline__ void apply4(const float4& d, const float4& fx, const 
     float e0, e1, e2, e3;
     upk(sub2(add2(lo2(nd), RAIN), EVAP), e0, e1);
     upk(sub2(add2(hi2(nd), RAIN), EVAP), e2, e3);
+    const float4 pre = nd;
     nd = make_float4(max0(e0), max0(e1), max0(e2), max0(e3));
+    if (ds != nullptr) *ds = make_float4(__fsub_rn(nd.x, pre.x), __fsub_rn(nd.y, pre.y), __fsub_rn(nd.z, pre.z), __fsub_rn(nd.w, pre.w));
+  } else if (ds != nullptr) {
+    *ds = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (VEL) {
     // vx = (iX1 - fx) - (iX0 - fy) (:45): inner differences on misaligned neighbours are scalar

@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(256) unfused_apply_kernel(Geom g, float* d, co
                                                             const float* __restrict__ Fym, uint32_t* __restrict__ v,
                                                             StepConsts c, int lr0, int lr1) {
   const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (x >= g.pitch) return;
-  for (int lr = lr0 + blockIdx.y; lr < lr1; lr += gridDim.y) {
+  double src_acc = 0.0;                                 // EXT ledger of the sources (whole warps reach the flush below)
+  for (int lr = lr0 + blockIdx.y; lr < lr1 && x < g.pitch; lr += gridDim.y) {
   const int gy = g.row0 + lr;
   const long long o = (long long)lr * g.pitch + x;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -89,14 +89,17 @@ __global__ void __launch_bounds__(256) unfused_apply_kernel(Geom g, float* d, co
   for (int i = 0; i < 4; ++i) {
     const float iX1 = (i < 3) ? comp(fy, i + 1) : r;
     const float iX0 = (i > 0) ? comp(fx, i - 1) : l;
-    float vx, vy;
-    nd[i] = apply_cell(comp(dC, i), comp(fx, i), comp(fy, i), comp(fz, i), comp(fw, i), iX1, iX0, comp(iy1, i), comp(iy0, i), c, vx, vy);
+    float vx, vy, ds;
+    nd[i] = apply_cell_src(comp(dC, i), comp(fx, i), comp(fy, i), comp(fz, i), comp(fw, i), iX1, iX0, comp(iy1, i), comp(iy0, i), c,
+                           c.ext_sources != 0, vx, vy, ds);
     nv[i] = pack_half2(vx, vy);
-    if (x + i >= g.W) { nd[i] = 0.f; nv[i] = 0u; }
+    if (x + i >= g.W) { nd[i] = 0.f; nv[i] = 0u; ds = 0.f; }
+    src_acc += (double)ds;
   }
   st4(d + o, make_float4(nd[0], nd[1], nd[2], nd[3]));
   *reinterpret_cast<uint4*>(v + o) = make_uint4(nv[0], nv[1], nv[2], nv[3]);
   }
+  if (c.ledger_src != nullptr) ledger_src_flush(c.ledger_src, src_acc);
 }
 
 // ------------------------------------------------------------------------------------
@@ -256,7 +259,7 @@ template <class C, bool EDGE, bool LAST, int IPT>
 __device__ __forceinline__ void depth_level(float* __restrict__ st, const int (&o)[IPT], const bool (&valid)[IPT], const float4 (&h)[IPT],
                                             float4 (&d)[IPT], const float4 (&fx)[IPT], const float4 (&fy)[IPT], const float4 (&fz)[IPT],
                                             const float4 (&fw)[IPT], const TileCtx& tc, const FusedOut& out, const Geom& g,
-                                            const StepConsts& c, const int lane, const int M) {
+                                            const StepConsts& c, const int lane, const int M, double& src_acc) {
   constexpr int SX = C::SX, PLANE = C::PLANE;
   float* sH = st + PLANE;
   const float* sFxp = st + 2 * PLANE; const float* sFxm = st + 3 * PLANE; const float* sFyp = st + 4 * PLANE; const float* sFym = st + 5 * PLANE;
@@ -273,22 +276,29 @@ __device__ __forceinline__ void depth_level(float* __restrict__ st, const int (&
     const int gy = tc.gy0 + r, gx0 = tc.sx0 + x;
     const bool row_in = (unsigned)gy < (unsigned)g.Hg;
     float nd[4]; uint32_t nv[4];
+    float4 ds4 = make_float4(0.f, 0.f, 0.f, 0.f);                                     // EXT ledger: what the sources changed
     if (!EDGE && TWS_PACKED) {
       float4 nd4; uint4 nv4 = make_uint4(0u, 0u, 0u, 0u);
-      apply4<LAST>(d[q], fx[q], fy[q], fz[q], fw[q], l, rgt, iy1, iy0, c, c.ext_sources != 0, nd4, nv4);
+      apply4<LAST>(d[q], fx[q], fy[q], fz[q], fw[q], l, rgt, iy1, iy0, c, c.ext_sources != 0, nd4, nv4, &ds4);
       nd[0] = nd4.x; nd[1] = nd4.y; nd[2] = nd4.z; nd[3] = nd4.w;
       nv[0] = nv4.x; nv[1] = nv4.y; nv[2] = nv4.z; nv[3] = nv4.w;
     } else {
+      float* pds = &ds4.x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float iX1 = (i < 3) ? comp(fy[q], i + 1) : rgt;
       const float iX0 = (i > 0) ? comp(fx[q], i - 1) : l;
       float vx, vy;
-      nd[i] = apply_cell(comp(d[q], i), comp(fx[q], i), comp(fy[q], i), comp(fz[q], i), comp(fw[q], i), iX1, iX0, comp(iy1, i),
-                         comp(iy0, i), c, vx, vy);
+      nd[i] = apply_cell_src(comp(d[q], i), comp(fx[q], i), comp(fy[q], i), comp(fz[q], i), comp(fw[q], i), iX1, iX0, comp(iy1, i),
+                             comp(iy0, i), c, c.ext_sources != 0, vx, vy, pds[i]);
       if (LAST) nv[i] = pack_half2(vx, vy);
-      if (EDGE && !(row_in && (unsigned)(gx0 + i) < (unsigned)g.W)) { nd[i] = 0.f; if (LAST) nv[i] = 0u; }
+      if (EDGE && !(row_in && (unsigned)(gx0 + i) < (unsigned)g.W)) { nd[i] = 0.f; pds[i] = 0.f; if (LAST) nv[i] = 0u; }
     }
+    }
+    if (c.ledger_src != nullptr) {                     // every sub-step, the tile's own output cells only
+      bool own = valid[q] && x >= C::HX && x < C::HX + C::OX && r >= C::HY && r < C::HY + C::OY;
+      if (EDGE) own = own && tc.ly0 + r < g.rows && gx0 < g.pitch;
+      if (own) src_acc += ((double)ds4.x + (double)ds4.y) + ((double)ds4.z + (double)ds4.w);
     }
     if (!LAST) {
       const bool live = valid[q] && r >= C::HY - M && r < C::HY + C::OY + M;
@@ -314,6 +324,7 @@ __device__ __forceinline__ void run_tile(float* st, const TileCtx& tc, const Fus
   static_assert(IPT <= 2, "tile too large for the register-resident scheme");
   static_assert(2 * NG <= NT, "halo rows are handled by the first 2*NG threads");
   const int lane = tid & 31;
+  double src_acc = 0.0;                                // EXT ledger of the sources, flushed once per tile
   float* sh = st; float* sd = st + PLANE;
   int o[IPT]; bool valid[IPT];
   float4 h[IPT], d[IPT], fx[IPT], fy[IPT], fz[IPT], fw[IPT];
@@ -339,12 +350,13 @@ __device__ __forceinline__ void run_tile(float* st, const TileCtx& tc, const Fus
   for (int t = 1; t < K; ++t) {
     flux_level<C, EDGE, false, IPT>(st, o, valid, h, d, fx, fy, fz, fw, tc, out, g, c, lane, 2 * (K - t) + 1);
     __syncthreads();
-    depth_level<C, EDGE, false, IPT>(st, o, valid, h, d, fx, fy, fz, fw, tc, out, g, c, lane, 2 * (K - t));
+    depth_level<C, EDGE, false, IPT>(st, o, valid, h, d, fx, fy, fz, fw, tc, out, g, c, lane, 2 * (K - t), src_acc);
     __syncthreads();
   }
   flux_level<C, EDGE, true, IPT>(st, o, valid, h, d, fx, fy, fz, fw, tc, out, g, c, lane, 1);
   __syncthreads();
-  depth_level<C, EDGE, true, IPT>(st, o, valid, h, d, fx, fy, fz, fw, tc, out, g, c, lane, 0);
+  depth_level<C, EDGE, true, IPT>(st, o, valid, h, d, fx, fy, fz, fw, tc, out, g, c, lane, 0, src_acc);
+  if (c.ledger_src != nullptr) ledger_src_flush(c.ledger_src, src_acc);
 }
 
 template <class C>

@@ -192,14 +192,8 @@ __device__ __forceinline__ void x_neighbours(const float (&w3)[G], const float (
 // flowApply.comp:38-46 with the source/sink extension compiled in or out.
 template <bool EXT>
 __device__ __forceinline__ float apply_cell_t(float depth, float fx, float fy, float fz, float fw, float iX1, float iX0, float iY1,
-                                              float iY0, const StepConsts& c, float& vx, float& vy) {
-  const float in = __fadd_rn(__fadd_rn(__fadd_rn(iX1, iX0), iY1), iY0);              // :38
-  const float out = __fadd_rn(__fadd_rn(__fadd_rn(fx, fy), fz), fw);                 // :39
-  float nd = max0(__fadd_rn(depth, __fmul_rn(__fsub_rn(in, out), c.area_inv)));      // :41
-  if (EXT) nd = max0(__fsub_rn(__fadd_rn(nd, c.rain_step), c.evap_step));            // EXT (same expression as apply_cell)
-  vx = __fsub_rn(__fsub_rn(iX1, fx), __fsub_rn(iX0, fy));                            // :45
-  vy = __fsub_rn(__fsub_rn(iY1, fz), __fsub_rn(iY0, fw));                            // :46
-  return nd;
+                                              float iY0, const StepConsts& c, float& vx, float& vy, float& ds) {
+  return apply_cell_src(depth, fx, fy, fz, fw, iX1, iX0, iY1, iY0, c, EXT, vx, vy, ds);
 }
 
 // flowUpdate.comp:34-62 for the lane's 4*G cells.  Reads the neighbour rows' water level, leaves the
@@ -289,7 +283,7 @@ template <int G, int SXW, bool EDGE, bool LAST, bool EXT>
 __device__ __forceinline__ void stream_depth(const uint32_t up, const uint32_t dn, const uint32_t me, const int lane,
                                              const float4 (&h)[G], float4 (&d)[G], const float4 (&fx)[G], const float4 (&fy)[G],
                                              const float4 (&fz)[G], const float4 (&fw)[G], const RowCtx<G>& rc, const FusedOut& out,
-                                             const Geom& g, const StepConsts& c) {
+                                             const Geom& g, const StepConsts& c, double& src_acc) {
   float4 iy1[G], iy0[G];
   float w3[G], x0[G], l[G], r[G];
 #pragma unroll
@@ -303,23 +297,26 @@ __device__ __forceinline__ void stream_depth(const uint32_t up, const uint32_t d
 #pragma unroll
   for (int q = 0; q < G; ++q) {
     float nd[4]; uint32_t nv[4];
+    float4 ds4 = make_float4(0.f, 0.f, 0.f, 0.f);                                     // EXT ledger: what the sources changed
     if (!EDGE && TWS_PACKED) {
       float4 nd4; uint4 nv4 = make_uint4(0u, 0u, 0u, 0u);
-      apply4<LAST>(d[q], fx[q], fy[q], fz[q], fw[q], l[q], r[q], iy1[q], iy0[q], c, EXT, nd4, nv4);
+      apply4<LAST>(d[q], fx[q], fy[q], fz[q], fw[q], l[q], r[q], iy1[q], iy0[q], c, EXT, nd4, nv4, EXT ? &ds4 : nullptr);
       nd[0] = nd4.x; nd[1] = nd4.y; nd[2] = nd4.z; nd[3] = nd4.w;
       nv[0] = nv4.x; nv[1] = nv4.y; nv[2] = nv4.z; nv[3] = nv4.w;
     } else {
+      float* pds = &ds4.x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float iX1 = (i < 3) ? comp(fy[q], i + 1) : r[q];
       const float iX0 = (i > 0) ? comp(fx[q], i - 1) : l[q];
       float vx, vy;
       nd[i] = apply_cell_t<EXT>(comp(d[q], i), comp(fx[q], i), comp(fy[q], i), comp(fz[q], i), comp(fw[q], i), iX1, iX0, comp(iy1[q], i),
-                                comp(iy0[q], i), c, vx, vy);
+                                comp(iy0[q], i), c, vx, vy, pds[i]);
       if (LAST) nv[i] = pack_half2(vx, vy);
-      if (EDGE && !(rc.row_in && (unsigned)(rc.gx[q] + i) < (unsigned)g.W)) { nd[i] = 0.f; if (LAST) nv[i] = 0u; }
+      if (EDGE && !(rc.row_in && (unsigned)(rc.gx[q] + i) < (unsigned)g.W)) { nd[i] = 0.f; pds[i] = 0.f; if (LAST) nv[i] = 0u; }
     }
     }
+    if (EXT && rc.store && rc.st[q]) src_acc += ((double)ds4.x + (double)ds4.y) + ((double)ds4.z + (double)ds4.w);   // every sub-step, owner lanes only
     if (!LAST) {
       d[q] = make_float4(nd[0], nd[1], nd[2], nd[3]);
       sts4(me + 512 * q, add4(d[q], h[q]));
@@ -342,6 +339,7 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
   __shared__ uint32_t progress[NW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wup = (warp + NW - 1) % NW, wdn = (warp + 1) % NW;
+  double src_acc = 0.0;                                 // EXT ledger of the sources: per-thread partial sum, flushed at the end
 
   // lane-resolved pointers: landing buffer; exchange slots [NW][H | F+Y | F-Y][SXW] of this row and its neighbours
   float* land = smem + warp * LAND;
@@ -459,14 +457,14 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
           stream_flux<G, SXW, false, false>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
           sy.signal(lane);
           sy.wait();
-          stream_depth<G, SXW, false, false, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+          stream_depth<G, SXW, false, false, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c, src_acc);
           sy.signal(lane);
         }
         sy.wait();
         stream_flux<G, SXW, false, true>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
         sy.signal(lane);
         sy.wait();
-        stream_depth<G, SXW, false, true, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+        stream_depth<G, SXW, false, true, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c, src_acc);
         sy.signal(lane);
       } else {
         // ---- rows on the grid edge (exterior masks, boundary mode) and feeder rows that stop early ----
@@ -479,8 +477,8 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
             if (last) stream_flux<G, SXW, true, true>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
             else stream_flux<G, SXW, true, false>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
           } else {
-            if (last) stream_depth<G, SXW, true, true, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
-            else stream_depth<G, SXW, true, false, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+            if (last) stream_depth<G, SXW, true, true, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c, src_acc);
+            else stream_depth<G, SXW, true, false, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c, src_acc);
           }
           sy.signal(lane);
         }
@@ -492,6 +490,7 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
     }
     turn_base += (uint32_t)turns;
   }
+  if (EXT) ledger_src_flush(c.ledger_src, src_acc);
 }
 
 // ---- host side ---------------------------------------------------------------------------

@@ -144,6 +144,7 @@ void derive_constants(tws_sim* s) {
   s->consts.ext_sources = (s->consts.rain_step != 0.0f || s->consts.evap_step != 0.0f) ? 1 : 0;
   s->consts.closed = (p.boundary == TWS_BOUNDARY_CLOSED) ? 1 : 0;
   s->consts.ledger = (s->ctrl != nullptr && !s->consts.closed) ? &s->ctrl->outflow_acc : nullptr;   // EXT mass ledger
+  s->consts.ledger_src = (s->ctrl != nullptr && s->consts.ext_sources) ? &s->ctrl->source_acc : nullptr;
 }
 
 bool bad_float(float v) { return !(v == v) || std::isinf(v); }
@@ -718,6 +719,7 @@ tws_status tws_reset_reference_scene_tiled(tws_sim* s, uint32_t seed, float heig
   s->launches += 1;
   s->accumulator = 0.0;
   TWS_CUDA(s, cudaMemsetAsync(&s->ctrl->outflow_acc, 0, sizeof(double), s->st_main));   // a new scene starts a new ledger
+  TWS_CUDA(s, cudaMemsetAsync(&s->ctrl->source_acc, 0, sizeof(double), s->st_main));
   TWS_CUDA(s, cudaStreamSynchronize(s->st_main));
   return TWS_OK;
 }
@@ -953,10 +955,20 @@ tws_status tws_boundary_outflow_accumulated(tws_sim* s, double* volume) {
   return TWS_OK;
 }
 
+tws_status tws_source_accumulated(tws_sim* s, double* volume) {
+  if (!s || !volume) return TWS_ERR_INVALID;
+  DeviceGuard guard(s->prm.device);
+  tws_status r = sync_all(s);
+  if (r) return r;
+  TWS_CUDA(s, cudaMemcpy(volume, &s->ctrl->source_acc, sizeof(double), cudaMemcpyDeviceToHost));
+  return TWS_OK;
+}
+
 tws_status tws_boundary_outflow_reset(tws_sim* s) {
   if (!s) return TWS_ERR_INVALID;
   DeviceGuard guard(s->prm.device);
   TWS_CUDA(s, cudaMemsetAsync(&s->ctrl->outflow_acc, 0, sizeof(double), s->st_main));
+  TWS_CUDA(s, cudaMemsetAsync(&s->ctrl->source_acc, 0, sizeof(double), s->st_main));
   return TWS_OK;
 }
 

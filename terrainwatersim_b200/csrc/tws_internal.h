@@ -41,6 +41,11 @@ struct Control {
   // reading 0).  Accumulated by the step kernels themselves (atomicAdd from the lanes that own an edge cell), so it is
   // exact for k steps per launch, where the intermediate fluxes never reach HBM.
   alignas(128) double outflow_acc;
+  // ... and what rain / evaporation REALLY added: fp64 sum over every owned cell and sub-step of (depth after the source
+  // terms - depth before them) as computed in fp32.  d + rain_step - evap_step rounds the same way for every cell of a
+  // binade, so the applied source differs systematically (up to ~1e-4 relative over 10 000 steps) from rate x time x area;
+  // a ledger that is to close has to book what the arithmetic did.
+  alignas(128) double source_acc;
 };
 
 static_assert(sizeof(Control) <= TWS_CTRL_BYTES, "the control block must fit in front of the planes");
@@ -51,6 +56,7 @@ struct StepConsts {
   int   closed;                      // EXT boundary
   int   ext_sources;                 // rain_step != 0 || evap_step != 0
   double* ledger;                    // EXT: &Control::outflow_acc, or nullptr (closed boundary: nothing can leave)
+  double* ledger_src;                // EXT: &Control::source_acc, or nullptr (no sources)
 };
 
 // Geometry handed to every kernel.

@@ -191,6 +191,13 @@ class Terrain:
         self._check(self._lib.tws_boundary_outflow_accumulated(self._sim, C.byref(v)))
         return float(v.value)
 
+    def source_accumulated(self) -> float:
+        """Volume rain and evaporation really changed since creation / reset (fp64 sum of the fp32 source deltas, accumulated
+        inside the step kernels)."""
+        v = C.c_double(0)
+        self._check(self._lib.tws_source_accumulated(self._sim, C.byref(v)))
+        return float(v.value)
+
     def boundary_outflow_reset(self) -> None:
         self._check(self._lib.tws_boundary_outflow_reset(self._sim))
 

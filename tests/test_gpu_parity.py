@@ -319,23 +319,46 @@ def test_boundary_outflow_accumulated_in_kernel_matches_oracle(tws, oracle, W, H
         assert sim.boundary_outflow_accumulated() == 0.0
 
 
-@pytest.mark.parametrize("name,backend,k", [BACKENDS[1], BACKENDS[4], BACKENDS[8], BACKENDS[12]])
+@pytest.mark.parametrize("name,backend,k", BACKENDS)
 def test_ledger_with_rain_and_evaporation_closes(tws, oracle, name, backend, k):
-    """SURVEY 8d config 5 in small: V(t) = V0 + rain - evaporation - boundary outflow, with the net source taken from
-    the oracle (evaporation is clamped at dry cells, so it is not rate x area) and the outflow from the in-kernel ledger."""
+    """SURVEY 8d config 5 in small: V(t) = V0 + sources - boundary outflow, BOTH sides booked inside the step kernels in
+    fp64: the outflow through the open edge, and what rain / evaporation really changed in fp32 (not rate x time x area:
+    d + rain_step - evap_step rounds alike for every cell of a binade, and evaporation is clamped at dry cells).  Each is
+    compared with the oracle's own per-step sum; together they close the volume balance."""
     W, H = 250, 190
     h, d = dam_break(W, H, rim=False)
     c = oracle.derive_consts(float(W), W)
-    rain, evap = 0.6, 0.3
+    rain, evap = 0.6, 0.9                 # evaporation > rain: the clamp at dry cells is exercised
     dt = float(np.float32(1.0) / np.float32(60.0))
     rs, es = float(np.float32(dt * rain)), float(np.float32(dt * evap))
     t, f, v = new_state(h, d)
     with make_sim(tws, W, H, backend, k, rain_rate=rain, evaporation_rate=evap) as sim:
         sim.upload(tws.FIELD_TERRAIN, h); sim.upload(tws.FIELD_WATER, d)
-        sim.step(60)
-        want = _oracle_outflow_per_step(oracle, t, f, v, c, 60, rs, es)
-        assert sim.boundary_outflow_accumulated() == pytest.approx(want, rel=1e-12)
+        vol0 = sim.total_volume()
+        assert sim.source_accumulated() == 0.0
+        want_out = want_src = 0.0
+        for n in (1, 6, 4 * k, 37):
+            sim.step(n)
+            for _ in range(n):
+                oracle.flow_update(t, f, c)
+                want_out += float(f[:, -1, 0].sum(dtype=np.float64) + f[:, 0, 1].sum(dtype=np.float64) + f[-1, :, 2].sum(dtype=np.float64)
+                                  + f[0, :, 3].sum(dtype=np.float64)) * float(c[2])
+                t0 = t.copy(); v0 = v.copy()
+                oracle.flow_apply(t0, f, v0, c)                       # the same pass without the source terms
+                oracle.flow_apply(t, f, v, c, rs, es)
+                want_src += float((t[..., 3].astype(np.float64) - t0[..., 3].astype(np.float64)).sum())
+            assert sim.boundary_outflow_accumulated() == pytest.approx(want_out, rel=1e-12)
+            assert sim.source_accumulated() == pytest.approx(want_src, rel=1e-11, abs=1e-9)
         assert_state_equal(sim, tws, t, f, v, name)
+        assert want_src < 0 and abs(want_src - W * H * 50 * (rs - es)) > 1e-3 * abs(want_src)   # NOT rate x time x area
+        vol = sim.total_volume()
+        assert abs(vol - (vol0 + sim.source_accumulated() - sim.boundary_outflow_accumulated())) / vol0 < 1e-6
+        sim.boundary_outflow_reset()
+        assert sim.source_accumulated() == 0.0 and sim.boundary_outflow_accumulated() == 0.0
+    with make_sim(tws, W, H, backend, k) as sim:                      # no sources: nothing is booked
+        sim.upload(tws.FIELD_TERRAIN, h); sim.upload(tws.FIELD_WATER, d)
+        sim.step(5)
+        assert sim.source_accumulated() == 0.0
 
 
 def test_elapsed_ms_nowait_reads_the_previous_batch_without_blocking(tws):

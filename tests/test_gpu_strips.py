@@ -176,6 +176,51 @@ def test_two_process_ipc(tws, tmp_path):
 
 
 @pytest.mark.parametrize("k,backend", [(4, 5), (2, 3), (3, 4)])
+def test_strip_source_ledgers_add_up(tws, oracle, k, backend):
+    """Rain + evaporation on strips: every strip books the source deltas of its own rows; together they are the oracle's sum."""
+    W, H, nstrips, steps = 200, 96, 3, 24
+    h, d = bumpy(W, H, seed=9)
+    c = oracle.derive_consts(float(W), W)
+    dt = float(np.float32(1.0) / np.float32(60.0))
+    rain, evap = 0.5, 1.5
+    rs, es = float(np.float32(dt * np.float32(rain))), float(np.float32(dt * np.float32(evap)))
+    t, f, v = new_state(h, d)
+    plan = tws.plan_strips(H, nstrips)
+    sims = [tws.Terrain(W, height=H, rows=plan.rows(i), backend=backend, temporal_block=k, device=0, rain_rate=rain, evaporation_rate=evap)
+            for i in range(nstrips)]
+    try:
+        handles = [s.halo_export() for s in sims]
+        for i, s in enumerate(sims):
+            s.halo_connect(handles[i - 1] if i > 0 else None, handles[i + 1] if i + 1 < nstrips else None)
+        for i, s in enumerate(sims):
+            r0, r1 = plan.rows(i)
+            s.upload(tws.FIELD_TERRAIN, h[r0:r1]); s.upload(tws.FIELD_WATER, d[r0:r1])
+        for s in sims:
+            s.halo_refresh()
+        for s in sims:
+            s.sync()
+        done = 0
+        while done < steps:
+            n = min(4, steps - done)
+            for s in sims:
+                s.step(n)
+            done += n
+        want = 0.0
+        for _ in range(steps):
+            oracle.flow_update(t, f, c)
+            t0 = t.copy(); v0 = v.copy()
+            oracle.flow_apply(t0, f, v0, c)
+            oracle.flow_apply(t, f, v, c, rs, es)
+            want += float((t[..., 3].astype(np.float64) - t0[..., 3].astype(np.float64)).sum())
+        assert sum(s.source_accumulated() for s in sims) == pytest.approx(want, rel=1e-11)
+        got = np.concatenate([s.readback(tws.FIELD_WATER) for s in sims])
+        assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(t[..., 3]).view(np.uint32))
+    finally:
+        for s in sims:
+            s.close()
+
+
+@pytest.mark.parametrize("k,backend", [(4, 5), (2, 3), (3, 4)])
 def test_strip_ledgers_add_up_to_the_whole_grid_ledger(tws, oracle, k, backend):
     """Each strip counts the outflow through ITS part of the global edge (both side columns, row 0 only on the first strip,
     the last row only on the last); the per-strip ledgers add up to the oracle's whole-grid sum."""
