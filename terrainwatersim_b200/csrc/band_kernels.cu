@@ -75,13 +75,7 @@ struct BandRow {       // per-row context (the lane's column offset and store ma
 // products before the wait, scaling of the unpublished components and the HBM stores after the arrive)
 // runs while the other warps catch up.  Every warp alternates arrive / wait strictly, so a single
 // barrier and one phase bit per thread suffice (nobody can arrive for phase n+1 before it has seen
-// phase n complete).  TWS_BAND_SPLIT 0 degrades it to a plain barrier (arrive + wait back to back).
-#ifndef TWS_BAND_PACKED_SCALE
-#define TWS_BAND_PACKED_SCALE 1
-#endif
-#ifndef TWS_BAND_SPLIT
-#define TWS_BAND_SPLIT 1
-#endif
+// phase n complete).
 struct GroupSync {
   uint32_t bar;        // shared address of the group's mbarrier
   uint32_t phase;      // parity of the phase the next wait() waits for
@@ -89,9 +83,8 @@ struct GroupSync {
     __syncwarp();                                         // every lane's shared-memory stores are ordered before the release
     asm volatile(
         "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\n@p mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n}" ::"r"(bar) : "memory");
-    if (!TWS_BAND_SPLIT) wait_now();
   }
-  __device__ __forceinline__ void wait() { if (TWS_BAND_SPLIT) wait_now(); }
+  __device__ __forceinline__ void wait() { wait_now(); }
   // Four polls per pass of the loop, and only a failed fourth one pays for the hang guard: a waiting warp shares its
   // scheduler with working ones, so every instruction of the wait loop is taken from a row that could make progress
   // (round-1 ncu: ~6 wake-ups per wait at 7 instructions each were 30 % of all issued instructions; now 2 per poll
@@ -240,7 +233,7 @@ __device__ __forceinline__ void band_flux(GroupSync& sy, const uint32_t (&up)[R]
   // a barrier — tests/test_abi.py checks that ptxas did not contract any of them into an FFMA2)
 #pragma unroll
   for (int q = 0; q < R; ++q) {
-    if (!EDGE && TWS_PACKED && TWS_BAND_PACKED_SCALE) {
+    if (!EDGE && TWS_PACKED) {
       const f2 slo = pk(scale[q][0], scale[q][1]), shi = pk(scale[q][2], scale[q][3]);
       fz[q] = cat4(mul2(lo2(fz[q]), slo), mul2(hi2(fz[q]), shi));
       fw[q] = cat4(mul2(lo2(fw[q]), slo), mul2(hi2(fw[q]), shi));
@@ -258,7 +251,7 @@ __device__ __forceinline__ void band_flux(GroupSync& sy, const uint32_t (&up)[R]
   sy.arrive();
 #pragma unroll
   for (int q = 0; q < R; ++q) {
-    if (!EDGE && TWS_PACKED && TWS_BAND_PACKED_SCALE) {
+    if (!EDGE && TWS_PACKED) {
       const f2 slo = pk(scale[q][0], scale[q][1]), shi = pk(scale[q][2], scale[q][3]);
       fx[q] = cat4(mul2(lo2(fx[q]), slo), mul2(hi2(fx[q]), shi));
       fy[q] = cat4(mul2(lo2(fy[q]), slo), mul2(hi2(fy[q]), shi));

@@ -43,43 +43,18 @@ struct StreamCfg {
 };
 
 // ------------------------------------------------------------------------------------------
-// Neighbour synchronisation.  Two interchangeable mechanisms (TWS_STREAM_WAIT):
-//   4 (default) — event mbarriers: one mbarrier per (slot, half-pass, ring-turn parity), arrived on
-//     once per row, so a barrier completes once every second row of its slot and its phase parity
-//     is bit 1 of the slot's ring-turn count.  A waiting warp sleeps in hardware
-//     (mbarrier.try_wait with a suspend-time hint) and costs no issue slots.  A parity wait is
-//     exact only while the awaited phase is the one in progress or the one just completed, i.e.
-//     while the neighbour slot is less than two ring turns away from the awaited row in either
-//     direction — which the dependency structure guarantees (with a single barrier per (slot,
-//     half-pass) it does not: in the first turn slot 0 can be a whole turn behind or ahead of the
-//     last slot).  Every slot arrives on all of its barriers in every ring turn of a piece, also
-//     for half-passes a row skips, so the phase counts are a pure function of the turn count and the
-//     barriers live across pieces.  tests/test_stream_protocol.py model-checks this protocol.
-//   0 — progress words: each slot publishes `rows done * NHP + half-passes done` (st.release) and
-//     a waiting warp polls its two neighbours' words (ld.acquire, broadcast LDS).
+// Neighbour synchronisation: event mbarriers.  One mbarrier per (slot, half-pass, ring-turn parity), arrived on once per
+// row, so a barrier completes once every second row of its slot and its phase parity is bit 1 of the slot's ring-turn
+// count.  A waiting warp sleeps in hardware (mbarrier.try_wait with a suspend-time hint).  A parity wait is exact only
+// while the awaited phase is the one in progress or the one just completed, i.e. while the neighbour slot is less than two
+// ring turns away from the awaited row in either direction — which the dependency structure guarantees (with a single
+// barrier per (slot, half-pass) it does not: in the first turn slot 0 can be a whole turn behind or ahead of the last
+// slot).  Every slot arrives on all of its barriers in every ring turn of a piece, also for half-passes a row skips, so
+// the phase counts are a pure function of the turn count and the barriers live across pieces.
+// tests/test_stream_protocol.py model-checks this protocol.
 // ------------------------------------------------------------------------------------------
-#ifndef TWS_STREAM_WAIT
-#define TWS_STREAM_WAIT 5
-#endif
-#define TWS_STREAM_EVT (TWS_STREAM_WAIT == 4 || TWS_STREAM_WAIT == 5)   // event-mbarrier protocol (5: tight single-barrier wait loops)
-#ifndef TWS_STREAM_SUSPEND_NS
-#define TWS_STREAM_SUSPEND_NS 20000
-#endif
-#ifndef TWS_STREAM_NOHINT
-#define TWS_STREAM_NOHINT 0    // 1: try_wait without a suspend-time hint (hardware default time limit)
-#endif
-#ifndef TWS_STREAM_L2PROMO
-#define TWS_STREAM_L2PROMO 0   // 0: none, 1: 128 B, 2: 256 B
-#endif
+constexpr uint32_t kStreamSuspendNs = 20000;   // suspend-time hint of the neighbour waits
 
-__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
-  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint32_t addr) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
@@ -87,8 +62,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t addr) {
 // Per-row synchronisation cursor: advanced by one half-pass per wait() / signal().
 struct RowSync {
   uint32_t up, dn, me;    // shared-memory addresses: neighbours' event barrier (or progress word), own
-  uint32_t pu, pd;        // mode 4: awaited phase parities; mode 0: awaited progress values
-  uint32_t val;           // mode 0: own next progress value
+  uint32_t pu, pd;        // awaited phase parities
   bool up_on;             // false for the first row of a piece (nobody above)
 
   // rows idx-1 and idx+1 have finished the half-pass before the one about to run
@@ -103,61 +77,28 @@ struct RowSync {
         ".reg .u32 n;\n"
         "mov.u32 n, 0;\n"
         "TWS_WAIT_LOOP:\n"
-#if TWS_STREAM_NOHINT
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-#endif
         "@p bra TWS_WAIT_DONE;\n"
         "add.u32 n, n, 1;\n"
         "setp.gt.u32 q, n, 4194304;\n"
         "@q trap;\n"
         "bra TWS_WAIT_LOOP;\n"
         "TWS_WAIT_DONE:\n"
-        "}\n" ::"r"(bar), "r"(par), "r"((uint32_t)TWS_STREAM_SUSPEND_NS) : "memory");
+        "}\n" ::"r"(bar), "r"(par), "r"(kStreamSuspendNs) : "memory");
   }
 
   __device__ __forceinline__ void wait() {
-    uint32_t spins = 0;
-#if TWS_STREAM_WAIT == 5
     // the row below is the one that lags (it started later); the row above is almost always done
     wait_one(dn, pd);
     if (up_on) wait_one(up, pu);
-    up += 16; dn += 16;
-    (void)spins;
-#elif TWS_STREAM_WAIT == 4
-    uint32_t done;
-    const uint32_t a = up_on ? up : dn, pa = up_on ? pu : pd;
-    do {
-      asm volatile(
-          "{\n"
-          ".reg .pred p, q;\n"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %5;\n"
-          "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4, %5;\n"
-          "and.pred p, p, q;\n"
-          "selp.u32 %0, 1, 0, p;\n"
-          "}\n" : "=r"(done) : "r"(a), "r"(pa), "r"(dn), "r"(pd), "r"((uint32_t)TWS_STREAM_SUSPEND_NS) : "memory");
-      if (!done && ++spins > (1u << 20)) __trap();      // a wait that never completes is a bug; a trap beats a hung GPU
-    } while (!done);
     up += 16; dn += 16;                                  // evt[slot][s][turn & 1] -> evt[slot][s + 1][turn & 1]
-#else
-    while ((up_on && ld_acquire_shared(up) < pu) || ld_acquire_shared(dn) < pd) {
-      if (++spins > (1u << 27)) __trap();
-    }
-    ++pu; ++pd;
-#endif
     __syncwarp();
   }
   // this row has finished a half-pass: every lane's shared-memory stores are ordered before the release
   __device__ __forceinline__ void signal(int lane) {
     __syncwarp();
-#if TWS_STREAM_EVT
     if (lane == 0) mbar_arrive(me);
     me += 16;
-#else
-    if (lane == 0) st_release_shared(me, val);
-    ++val;
-#endif
   }
 };
 
@@ -336,7 +277,6 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
   extern __shared__ __align__(1024) float smem[];
   __shared__ uint64_t full[NW];
   __shared__ __align__(16) uint64_t evt[NW][NHP][2];      // per slot, half-pass and ring-turn parity
-  __shared__ uint32_t progress[NW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wup = (warp + NW - 1) % NW, wdn = (warp + 1) % NW;
   double src_acc = 0.0;                                 // EXT ledger of the sources: per-thread partial sum, flushed at the end
@@ -377,7 +317,6 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
     const bool xedge = sx0 < 0 || sx0 + SXW > g.W;
 
     __syncthreads();                                      // every warp is done with the previous piece
-    if (tid < NW) progress[tid] = 0;
     __syncthreads();
 
     auto issue = [&](int y) {                             // one lane: land row y in this warp's buffer
@@ -403,24 +342,16 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
       const int idx = t * NW + warp;
       const uint32_t turn = turn_base + (uint32_t)t;
       RowSync sy;
-#if TWS_STREAM_EVT
       // neighbours' turns: the row above a slot-0 row lives in the previous turn, the row below a last-slot row in the next
       const uint32_t tu = warp == 0 ? turn - 1u : turn, td = warp == NW - 1 ? turn + 1u : turn;
       sy.up = smem_u32(&evt[wup][0][tu & 1u]); sy.pu = (tu >> 1) & 1u;
       sy.dn = smem_u32(&evt[wdn][0][td & 1u]); sy.pd = (td >> 1) & 1u;
       sy.me = smem_u32(&evt[warp][0][turn & 1u]);
-      sy.val = 0;
       if (idx >= nrows) {                                 // no row for this slot in the last turn: keep the phase counts uniform
         if (lane == 0)
           for (int e = 0; e < NHP; ++e) mbar_arrive(sy.me + 16 * e);
         break;
       }
-#else
-      if (idx >= nrows) break;
-      sy.up = smem_u32(&progress[wup]); sy.dn = smem_u32(&progress[wdn]); sy.me = smem_u32(&progress[warp]);
-      sy.pu = (uint32_t)(idx - 1) * NHP + 1u; sy.pd = (uint32_t)(idx + 1) * NHP + 1u;      // neighbour has finished half-pass 0
-      sy.val = (uint32_t)idx * NHP + 1u;
-#endif
       sy.up_on = idx > 0;
       const int y = ystart + idx;                         // local row
       rc.gy = g.row0 + y;
@@ -482,10 +413,8 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
           }
           sy.signal(lane);
         }
-#if TWS_STREAM_EVT
         if (lane == 0)                                    // the half-passes this feeder row skipped
           for (; s <= 2 * K; ++s) { mbar_arrive(sy.me); sy.me += 16; }
-#endif
       }
     }
     turn_base += (uint32_t)turns;
@@ -561,7 +490,7 @@ cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& t
 // Row descriptors: box = one SXW-cell row segment.  Same visibility rule as the tile kernel's maps
 // (own rows plus the halo rows towards an existing neighbour; everything else zero-filled).
 cudaError_t stream_build_tma(const Geom& g, const Planes& p, int side, TmaSet* out, std::string* err) {
-  return build_tma_rows(g, p, side, StreamCfgFor<1>::type::SXW, out, err, TWS_STREAM_L2PROMO);
+  return build_tma_rows(g, p, side, StreamCfgFor<1>::type::SXW, out, err, 0);
 }
 
 }  // namespace tws

@@ -400,6 +400,40 @@ def test_advice_r1_edge_cases(tws, oracle):
         assert sim.PerformSimulationStep(1.0) == 10          # the accumulator was not poisoned by the refused frame
 
 
+@pytest.mark.parametrize("name,backend,k", [BACKENDS[0], BACKENDS[4], BACKENDS[8], BACKENDS[12]])
+def test_cuda_path_against_the_reference_shaders_directly(tws, name, backend, k):
+    """No oracle in between: the CUDA library against the reference's OWN flowUpdate / flowApply / waterBrush shaders
+    (oracle/_ref/libtws_ref_step.so, compiled from /root/reference in the build container and shipped prebuilt) — BASELINE
+    config 1 for 300 steps and the 1024^2 reference scene with the brush before every step for 60 steps, bit for bit."""
+    from oracle.oracle_py import RefStep
+    try:
+        ref = RefStep()
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/libtws_ref_step.so not present on this box")
+    # config 1, open boundary (the reference's native behaviour)
+    h, d = dam_break(256, rim=False)
+    t, f, v = new_state(h, d)
+    with make_sim(tws, 256, 256, backend, k) as sim:
+        c = np.float32(sim.step_constants())
+        sim.upload(tws.FIELD_TERRAIN, h); sim.upload(tws.FIELD_WATER, d)
+        sim.step(300)
+        ref.step(t, f, v, c, 300)
+        assert_state_equal(sim, tws, t, f, v, name + " vs reference shaders, config 1")
+    # config 2: reference scene + brush (Scene.cpp:356-363)
+    with make_sim(tws, 1024, 1024, backend, k) as sim:
+        sim.CreateHeightmapFromNoiseAndResetSim()
+        c = np.float32(sim.step_constants())
+        t = sim.readback(tws.FIELD_TERRAIN_INFO)
+        f = np.zeros((1024, 1024, 4), np.float32); v = np.zeros((1024, 1024, 2), np.float16)
+        inten = np.float32(100.0 / 60.0)
+        for _ in range(60):
+            sim.inject_brush(512.0, 512.0, float(inten), 32.0)
+            sim.step(1)
+            ref.brush(t, 512.0, 512.0, inten, 32.0)
+            ref.step(t, f, v, c, 1)
+        assert_state_equal(sim, tws, t, f, v, name + " vs reference shaders, config 2")
+
+
 def test_parameter_validation_on_device(tws):
     with make_sim(tws, 64, 64, tws.BACKEND_FUSED, 1) as sim:
         for call in (lambda: sim.SetSimulationStepsPerSecond(0.0), lambda: sim.SetFlowDamping(-1.0), lambda: sim.SetFlowAcceleration(float("nan")),
