@@ -138,7 +138,12 @@ def load() -> C.CDLL:
             "(terrainwatersim_b200 has no CPU or pure-Python path)")
     lib = C.CDLL(str(path))
     for name, (res, args) in SYMBOLS.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            if "TWS_LIB" in os.environ:       # an older tuning build may predate an entry point; the product library may not
+                continue
+            raise
         fn.restype = res
         fn.argtypes = args
     _lib = lib

@@ -113,6 +113,29 @@ __device__ __forceinline__ void ledger_add(const StepConsts& c, const Geom& g, i
   }
   if (s != 0.0) atomicAdd(c.ledger, s * (double)c.area_inv);
 }
+// The same into a per-thread partial sum (flushed with ledger_src_flush at the end of the kernel): for the ring kernel, whose
+// static work split makes the launch as slow as its slowest column strip — an atomic per row of the two edge strips showed
+// up as 238 -> 185 Gcell/s at K = 3 (bisected, round 2).
+__device__ __forceinline__ void ledger_acc(double& acc, const StepConsts& c, const Geom& g, int gx0, int gy, const float4& fx, const float4& fy,
+                                           const float4& fz, const float4& fw) {
+  const bool ytop = gy == 0, ybot = gy == g.Hg - 1;
+  if ((unsigned)gy >= (unsigned)g.Hg || !(ytop || ybot || gx0 == 0 || gx0 + 3 >= g.W - 1)) return;
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = gx0 + i;
+    if ((unsigned)x >= (unsigned)g.W) continue;
+    const float px = i == 0 ? fx.x : (i == 1 ? fx.y : (i == 2 ? fx.z : fx.w));
+    const float py = i == 0 ? fy.x : (i == 1 ? fy.y : (i == 2 ? fy.z : fy.w));
+    const float pz = i == 0 ? fz.x : (i == 1 ? fz.y : (i == 2 ? fz.z : fz.w));
+    const float pw = i == 0 ? fw.x : (i == 1 ? fw.y : (i == 2 ? fw.z : fw.w));
+    if (x == g.W - 1) s += (double)px;
+    if (x == 0) s += (double)py;
+    if (ybot) s += (double)pz;
+    if (ytop) s += (double)pw;
+  }
+  acc += s * (double)c.area_inv;
+}
 
 __device__ __forceinline__ uint32_t pack_half2(float x, float y) {                  // rg16f store, :52
   const __half2 h = __floats2half2_rn(x, y);

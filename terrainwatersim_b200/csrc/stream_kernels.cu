@@ -143,7 +143,8 @@ __device__ __forceinline__ float apply_cell_t(float depth, float fx, float fy, f
 template <int G, int SXW, bool EDGE, bool LAST>
 __device__ __forceinline__ void stream_flux(const uint32_t up, const uint32_t dn, const uint32_t me, const int lane,
                                             const float4 (&h)[G], const float4 (&d)[G], float4 (&fx)[G], float4 (&fy)[G], float4 (&fz)[G],
-                                            float4 (&fw)[G], const RowCtx<G>& rc, const FusedOut& out, const Geom& g, const StepConsts& c) {
+                                            float4 (&fw)[G], const RowCtx<G>& rc, const FusedOut& out, const Geom& g, const StepConsts& c,
+                                            double& out_acc) {
   float4 HC[G], HU[G], HD[G];
   float w3[G], x0[G], HL[G], HR[G];
 #pragma unroll
@@ -210,7 +211,7 @@ __device__ __forceinline__ void stream_flux(const uint32_t up, const uint32_t dn
     }
     sts4(me + 4 * SXW + 512 * q, fz[q]);         // plane 1: +Y outflow, read by the row below
     sts4(me + 8 * SXW + 512 * q, fw[q]);         // plane 2: -Y outflow, read by the row above
-    if (EDGE && rc.store && rc.st[q]) ledger_add(c, g, rc.gx[q], rc.gy, fx[q], fy[q], fz[q], fw[q]);       // every sub-step, owner lanes only
+    if (EDGE && rc.store && rc.st[q]) ledger_acc(out_acc, c, g, rc.gx[q], rc.gy, fx[q], fy[q], fz[q], fw[q]);   // every sub-step, owner lanes only
     if (LAST && rc.store && rc.st[q]) {
       st4(out.F[0] + rc.go[q], fx[q]); st4(out.F[1] + rc.go[q], fy[q]); st4(out.F[2] + rc.go[q], fz[q]); st4(out.F[3] + rc.go[q], fw[q]);
     }
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wup = (warp + NW - 1) % NW, wdn = (warp + 1) % NW;
   double src_acc = 0.0;                                 // EXT ledger of the sources: per-thread partial sum, flushed at the end
+  double out_acc = 0.0;                                 // ... and of the boundary outflow (lanes that own an edge cell)
 
   // lane-resolved pointers: landing buffer; exchange slots [NW][H | F+Y | F-Y][SXW] of this row and its neighbours
   float* land = smem + warp * LAND;
@@ -385,14 +387,14 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
 #pragma unroll 1
         for (int lv = 1; lv < K; ++lv) {
           sy.wait();
-          stream_flux<G, SXW, false, false>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+          stream_flux<G, SXW, false, false>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c, out_acc);
           sy.signal(lane);
           sy.wait();
           stream_depth<G, SXW, false, false, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c, src_acc);
           sy.signal(lane);
         }
         sy.wait();
-        stream_flux<G, SXW, false, true>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+        stream_flux<G, SXW, false, true>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c, out_acc);
         sy.signal(lane);
         sy.wait();
         stream_depth<G, SXW, false, true, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c, src_acc);
@@ -405,8 +407,8 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
           sy.wait();
           const bool last = s >= 2 * K - 1;
           if (s & 1) {
-            if (last) stream_flux<G, SXW, true, true>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
-            else stream_flux<G, SXW, true, false>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c);
+            if (last) stream_flux<G, SXW, true, true>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c, out_acc);
+            else stream_flux<G, SXW, true, false>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c, out_acc);
           } else {
             if (last) stream_depth<G, SXW, true, true, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c, src_acc);
             else stream_depth<G, SXW, true, false, EXT>(x_up, x_dn, x_me, lane, h, d, fx, fy, fz, fw, rc, out, g, c, src_acc);
@@ -420,6 +422,7 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
     turn_base += (uint32_t)turns;
   }
   if (EXT) ledger_src_flush(c.ledger_src, src_acc);
+  ledger_src_flush(c.ledger, out_acc);
 }
 
 // ---- host side ---------------------------------------------------------------------------
