@@ -335,12 +335,36 @@ void tws_oracle_create_scene(uint32_t seed, int W, int H, float height_scale, in
       t.y = 0.3f; t.z = 0.3f;
       const float px = x * mx - 0.5f, py = y * my - 0.5f;
       const float l2 = px * px + py * py;                       // ezVec2::GetLengthSquared
-      const float p = powf(l2, 2.0f);                           // pow(float, 2.0f) — float overload
+      // Terrain.cpp:219 writes pow(l2, 2.0f) (float overload, SURVEY 8c pin 4).  PINNED to the product: g++ folds that very call
+      // to l2 * l2 when it compiles the reference's own generator (oracle/_ref agrees bit for bit), the CUDA scene kernel
+      // multiplies, and a library powf need not: glibc's differs from the product for 380 438 of the 1.06e9 binary32
+      // arguments in [0, 0.5] (tests/test_oracle.py::test_pow_squared_is_pinned_to_the_product).
+      const float p = l2 * l2;
       t.w = std::max(0.0f, (0.45f - p * 800.0f) * height_scale - t.x);
       out[(size_t)x + (size_t)y * W] = t;
     }
   }
   delete ng;
+}
+
+// Terrain.cpp:219 evaluates pow(lengthSquared, 2.0f); the CUDA scene kernel evaluates l2 * l2.  Counts the binary32 values in
+// [lo_bits, hi_bits] (as bit patterns of non-negative floats) for which this libm's powf(x, 2.0f) differs from x * x.
+uint64_t tws_oracle_pow2_mismatches(uint32_t lo_bits, uint32_t hi_bits) {
+  uint64_t bad = 0;
+  float (*volatile libm_powf)(float, float) = powf;     // through a volatile pointer: the library routine itself, not the
+                                                        // compiler's pow(x, 2) -> x * x folding (which g++ applies to the
+                                                        // oracle's and the reference generator's own call at Terrain.cpp:219)
+#if defined(_OPENMP)
+#pragma omp parallel for reduction(+ : bad) schedule(static)
+#endif
+  for (int64_t b = (int64_t)lo_bits; b <= (int64_t)hi_bits; ++b) {
+    const uint32_t u = (uint32_t)b;
+    float x; std::memcpy(&x, &u, 4);
+    const float p = libm_powf(x, 2.0f), m = x * x;
+    uint32_t pu, mu; std::memcpy(&pu, &p, 4); std::memcpy(&mu, &m, 4);
+    bad += (pu != mu) ? 1u : 0u;
+  }
+  return bad;
 }
 
 uint16_t tws_oracle_float_to_half(float f) { return float_to_half_rtne(f); }

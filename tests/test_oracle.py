@@ -74,7 +74,7 @@ def test_white_noise_table_equals_reference_random(oracle):
     assert -1.0 <= w.min() and w.max() <= 1.0
 
 
-@pytest.mark.parametrize("res", [64, 1024])
+@pytest.mark.parametrize("res", [64, 777, 1024])
 def test_scene_bit_equal_to_reference_compiled_generator(oracle_omp, res):
     ref = _ref_lib()
     a = np.zeros((res, res, 4), np.float32)
@@ -96,6 +96,23 @@ def test_scene_golden_and_survey_statistics(oracle_omp):
     assert h[0, 0] == h[1023, 1023] == f32(257.151459)          # period-1 noise
     assert h[511, 511] == f32(66.4997406) and d[512, 512] == f32(68.531517)
     assert np.all(s[..., 1] == f32(0.3)) and np.all(s[..., 2] == f32(0.3))
+
+
+def test_pow_squared_is_pinned_to_the_product(oracle_omp):
+    """Terrain.cpp:219 calls pow(l2, 2.0f) with l2 = |p - 0.5|^2 in [0, 0.5].  The oracle and the CUDA scene kernel evaluate
+    l2 * l2 — and so does the reference's own generator as g++ compiles it (the call is folded; oracle/_ref agrees bit for bit,
+    test_scene_bit_equal_to_reference_compiled_generator, also at a size that is no power of two).  That this is a PIN and not
+    an identity is checked exhaustively: over EVERY binary32 value in [0, 0.5] this libm's powf routine (called through a
+    volatile pointer, so nothing is folded) is within rounding of the product but not always equal to it."""
+    lib = oracle_omp.lib
+    lib.tws_oracle_set_threads(max(1, len(__import__("os").sched_getaffinity(0))))
+    lib.tws_oracle_pow2_mismatches.restype = C.c_uint64
+    lib.tws_oracle_pow2_mismatches.argtypes = [C.c_uint32, C.c_uint32]
+    half = int(np.float32(0.5).view(np.uint32))
+    total = half + 1
+    bad = lib.tws_oracle_pow2_mismatches(0, half)
+    assert bad < total // 1000                      # a (nearly) correctly rounded routine: equal for > 99.9 % of the arguments
+    assert lib.tws_oracle_pow2_mismatches(0, 0x00800000) == 0          # subnormal arguments: both underflow to 0
 
 
 # ---- a5/a6 micro cases (hand-derived from the shader text) ----------------------------------------
