@@ -518,7 +518,7 @@ def run_b200(args):
         S = args.strong_size
         ks = 4
         need_gb = 48.0 * S * S / 1e9 + 4.0
-        free_gb = torch.cuda.mem_get_info()[0] / 1e9
+        free_gb = -max_over_ranks(-torch.cuda.mem_get_info()[0] / 1e9)     # the least free memory of any rank: one decision for all
         if free_gb < need_gb:
             strong = {"skipped": f"{S}x{S} needs {need_gb:.0f} GB on one GPU for T1, {free_gb:.0f} GB free"}
         else:

@@ -8,7 +8,7 @@ import ctypes as C
 import terrainwatersim_b200 as tws
 
 for W in (256, 1024, 2048):
-    for name, b, k in (("unfused", 1, 1), ("tile k=2", 3, 2), ("band k=2", 5, 2), ("band k=4", 5, 4)):
+    for name, b, k in (("unfused", 1, 1), ("tile k=1", 2, 1), ("tile k=2", 3, 2), ("tile k=3", 3, 3), ("band k=2", 5, 2), ("band k=4", 5, 4)):
         with tws.Terrain(W, backend=b, temporal_block=k) as sim:
             sim.CreateHeightmapFromNoiseAndResetSim()
             for _ in range(20): sim.step(10)
@@ -16,7 +16,8 @@ for W in (256, 1024, 2048):
             t0 = time.perf_counter(); frames = 400
             for _ in range(frames): sim.step(10)
             sim.sync(); dt = time.perf_counter() - t0
-            print(f"small {W:5d} {name:10s} graphs={sim.graph_replays() > 0} {dt / frames * 1e6:8.1f} us/frame(10 steps) {W * W * 10 * frames / dt / 1e9:8.2f} Gcell/s launches={sim.kernel_launches()}", flush=True)
+            gpu_us = sim.elapsed_ms() * 1e3           # device time of the LAST 10-step batch alone (CUDA events)
+            print(f"small {W:5d} {name:10s} graphs={sim.graph_replays() > 0} {dt / frames * 1e6:8.1f} us/frame(10 steps) wall, {gpu_us:7.1f} us on the device, {W * W * 10 * frames / dt / 1e9:8.2f} Gcell/s launches={sim.kernel_launches()}", flush=True)
 
 # the reference's frame: ApplyRadialWaterBrush + PerformSimulationStep(1/60 s) (one step) + GenMipMaps
 for name, b, k in (("unfused", 1, 1), ("fused", 2, 1), ("band k=1", 5, 1)):
