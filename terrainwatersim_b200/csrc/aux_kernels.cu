@@ -248,6 +248,120 @@ __global__ void __launch_bounds__(1024) mip_tail_kernel(float4* base, int W, int
     __syncthreads();
   }
 }
+// Single-pass chain ("single-pass downsampler"): every CTA reduces its tile through six levels out of shared memory and the last
+// CTA to finish (device-wide ticket) reduces what is left, down to 1 x 1.  Same 2x2 box and operation order as
+// mip_level_kernel.  At the reference's own size (1024^2) the separate path took a pack launch, a copy, two mip launches and
+// a single-CTA tail that went back to L2 between its eight levels (22 us alone); the renderer hand-off runs every frame.
+__device__ __forceinline__ float4 mip_box(const float4& a, const float4& b, const float4& c, const float4& d) {
+  float4 o;
+  o.x = __fmul_rn(__fadd_rn(__fadd_rn(a.x, b.x), __fadd_rn(c.x, d.x)), 0.25f);
+  o.y = __fmul_rn(__fadd_rn(__fadd_rn(a.y, b.y), __fadd_rn(c.y, d.y)), 0.25f);
+  o.z = __fmul_rn(__fadd_rn(__fadd_rn(a.z, b.z), __fadd_rn(c.z, d.z)), 0.25f);
+  o.w = __fmul_rn(__fadd_rn(__fadd_rn(a.w, b.w), __fadd_rn(c.w, d.w)), 0.25f);
+  return o;
+}
+// The last CTA of a single-pass chain kernel: levels [first, nlevels) from level first-1 (cw x ch texels at texel offset soff),
+// written by OTHER CTAs (visible: they fenced before taking their ticket).  Levels that fit the two shared buffers (<= 1024 and
+// <= 256 texels) are reduced out of shared memory — no trip to L2 between them; larger ones go through global memory.
+__device__ __forceinline__ void mip_finish_chain(float4* base, long long soff, int cw, int ch, int first, int nlevels, float4* sa, float4* sb) {
+  const int tid = threadIdx.x;
+  bool in_smem = false;                                 // level first-1 sits in `cur` (shared) as well as in global memory
+  float4* cur = sa; float4* nxt = sb;
+  for (int l = first; l < nlevels; ++l) {
+    const int nw = max(1, cw >> 1), nh = max(1, ch >> 1);
+    const float4* sp = base + soff;
+    float4* dp = base + soff + (long long)cw * ch;
+    if (!in_smem && cw * ch <= 1024 && nw * nh <= 256) {   // bring the source level into shared memory once
+      for (int i = tid; i < cw * ch; i += blockDim.x) sa[i] = __ldcg(sp + i);
+      cur = sa; nxt = sb; in_smem = true;
+      __syncthreads();
+    }
+    for (int i = tid; i < nw * nh; i += blockDim.x) {
+      const int x = i % nw, y = i / nw;
+      const int x0 = min(2 * x, cw - 1), x1 = min(2 * x + 1, cw - 1);
+      const int r0 = min(2 * y, ch - 1) * cw, r1 = min(2 * y + 1, ch - 1) * cw;
+      float4 o;
+      if (in_smem) { o = mip_box(cur[r0 + x0], cur[r0 + x1], cur[r1 + x0], cur[r1 + x1]); nxt[i] = o; }
+      else o = mip_box(__ldcg(sp + r0 + x0), __ldcg(sp + r0 + x1), __ldcg(sp + r1 + x0), __ldcg(sp + r1 + x1));
+      dp[i] = o;
+    }
+    if (!in_smem) __threadfence();
+    __syncthreads();
+    if (in_smem) { float4* t = cur; cur = nxt; nxt = t; }
+    soff += (long long)cw * ch;
+    cw = nw; ch = nh;
+  }
+}
+// The whole renderer hand-off of a whole grid whose sides are multiples of 64 in ONE launch: every CTA takes a 64 x 64 tile of
+// CELLS, writes its TerrainInfo level-0 texels and flow-map texels, reduces levels 1..6 of the tile (32^2 .. 1 texels; level 1
+// straight from the planar state, the rest out of shared memory), and the last CTA to finish reduces the remaining levels.
+__global__ void __launch_bounds__(256) publish_all_kernel(Geom g, const float* __restrict__ h, const float* __restrict__ d,
+                                                          const uint32_t* __restrict__ v, float4* base, uint32_t* __restrict__ flow, int W, int H,
+                                                          int nlevels, unsigned int* ticket) {
+  __shared__ float4 sa[32 * 32];
+  __shared__ float4 sb[16 * 16];
+  __shared__ unsigned int s_last;
+  const int tid = threadIdx.x, bx = blockIdx.x, by = blockIdx.y;
+  float4* l0 = base;
+  long long doff = (long long)W * H;                   // level 1
+  {
+    const int dw = W >> 1;
+    float4* l1 = base + doff;
+    for (int i = tid; i < 32 * 32; i += 256) {
+      const int x = i & 31, y = i >> 5;
+      const int cx = bx * 64 + 2 * x, cy = by * 64 + 2 * y;
+      const long long o00 = (long long)cy * g.pitch + cx, o10 = o00 + g.pitch;
+      const float2 h0 = *reinterpret_cast<const float2*>(h + o00), h1 = *reinterpret_cast<const float2*>(h + o10);
+      const float2 d0 = *reinterpret_cast<const float2*>(d + o00), d1 = *reinterpret_cast<const float2*>(d + o10);
+      const float4 a = make_float4(h0.x, 0.3f, 0.3f, d0.x), b = make_float4(h0.y, 0.3f, 0.3f, d0.y);
+      const float4 c = make_float4(h1.x, 0.3f, 0.3f, d1.x), e = make_float4(h1.y, 0.3f, 0.3f, d1.y);
+      const long long t00 = (long long)cy * W + cx;
+      l0[t00] = a; l0[t00 + 1] = b; l0[t00 + W] = c; l0[t00 + W + 1] = e;
+      *reinterpret_cast<uint2*>(flow + t00) = *reinterpret_cast<const uint2*>(v + o00);
+      *reinterpret_cast<uint2*>(flow + t00 + W) = *reinterpret_cast<const uint2*>(v + o10);
+      const float4 o = mip_box(a, b, c, e);
+      sa[i] = o;
+      l1[(long long)(by * 32 + y) * dw + bx * 32 + x] = o;
+    }
+  }
+  __syncthreads();
+  float4* cur = sa; float4* nxt = sb;
+  int cw = 32, lw = W >> 1, lh = H >> 1;
+  doff += (long long)lw * lh;
+#pragma unroll 1
+  for (int step = 2; step <= 6; ++step) {
+    const int nw = cw >> 1, dw = lw >> 1;
+    float4* dst = base + doff;
+    if (tid < nw * nw) {
+      const int x = tid % nw, y = tid / nw;
+      const float4 o = mip_box(cur[(2 * y) * cw + 2 * x], cur[(2 * y) * cw + 2 * x + 1], cur[(2 * y + 1) * cw + 2 * x], cur[(2 * y + 1) * cw + 2 * x + 1]);
+      nxt[y * nw + x] = o;
+      dst[(long long)(by * nw + y) * dw + bx * nw + x] = o;
+    }
+    __syncthreads();
+    float4* t = cur; cur = nxt; nxt = t;
+    cw = nw; lw = dw; lh >>= 1;
+    doff += (long long)lw * lh;
+  }
+  __threadfence();
+  if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1u) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  if (tid == 0) *ticket = 0u;
+  __threadfence();
+  mip_finish_chain(base, doff - (long long)lw * lh, lw, lh, 7, nlevels, sa, sb);
+}
+bool publish_all_applicable(const Geom& g, int nlevels) {
+  return !g.has_up && !g.has_down && g.W >= 64 && g.rows >= 64 && g.W % 64 == 0 && g.rows % 64 == 0 && nlevels >= 7;
+}
+cudaError_t launch_publish_all(const Geom& g, const Planes& p, int side, float* chain, uint32_t* flow, int nlevels, unsigned int* ticket,
+                               cudaStream_t st) {
+  const size_t off = (size_t)TWS_HALO_ROWS * g.pitch;
+  dim3 grid(g.W / 64, g.rows / 64);
+  publish_all_kernel<<<grid, 256, 0, st>>>(g, p.h + off, p.d[side] + off, p.v + off, (float4*)chain, flow, g.W, g.rows, nlevels, ticket);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_mip_tail(float* base, int W, int H, int first, int last, cudaStream_t st) {
   if (first >= last) return cudaSuccess;
   mip_tail_kernel<<<1, 1024, 0, st>>>((float4*)base, W, H, first, last);

@@ -1169,11 +1169,19 @@ int strip_mip_levels(const Geom& g) {
 tws_status publish_chain(tws_sim* s) {
   const Geom& g = s->geom;
   const int L = strip_mip_levels(g);
+  if (publish_all_applicable(g, L)) {                   // e.g. the reference's 1024^2: the whole hand-off is one launch
+    const size_t cells = (size_t)g.W * g.rows;
+    if (!s->packed_info) TWS_CUDA(s, cudaMalloc(&s->packed_info, mip_chain_texels(g.W, g.rows) * 16));
+    if (!s->packed_flow) TWS_CUDA(s, cudaMalloc(&s->packed_flow, cells * 4));
+    TWS_CUDA(s, launch_publish_all(g, s->planes, s->cur, (float*)s->packed_info, (uint32_t*)s->packed_flow, L, &s->ctrl->mip_ticket, s->st_main));
+    s->launches += 1;
+    s->published_levels = L;
+    return TWS_OK;
+  }
   tws_status r = publish_level0(s, L > 1);
   if (r) return r;
   float* base = (float*)s->packed_info;
-  // level 1 came with level 0; further large levels: one launch each; from the first level of <= 16 K texels on, the whole
-  // tail in one launch
+  // level 1 came with level 0; further large levels one launch each; from the first level of <= 16 K texels on, the whole tail in one launch
   int first_tail = L;
   for (int l = 2; l < L; ++l) {
     int32_t sw, sh, dw, dh; int64_t so, d_o;

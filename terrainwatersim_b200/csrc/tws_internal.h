@@ -46,6 +46,7 @@ struct Control {
   // binade, so the applied source differs systematically (up to ~1e-4 relative over 10 000 steps) from rate x time x area;
   // a ledger that is to close has to book what the arithmetic did.
   alignas(128) double source_acc;
+  alignas(128) uint32_t mip_ticket;  // CTAs of the mip chain's single-pass kernel that have finished (re-armed by the last one)
 };
 
 static_assert(sizeof(Control) <= TWS_CTRL_BYTES, "the control block must fit in front of the planes");
@@ -141,6 +142,11 @@ cudaError_t launch_pack_info(const Geom& g, const Planes& p, int side, float* ao
 cudaError_t launch_publish_fused(const Geom& g, const Planes& p, int side, float* level0, float* level1, uint32_t* flow, cudaStream_t st);
 // one level of the RGBA32F mip chain (2x2 box, see aux_kernels.cu): dst (dw x dh texels) <- src (sw x sh texels)
 cudaError_t launch_mip_level(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t st);
+// whole grids with sides that are multiples of 64: level 0, the flow map and EVERY mip level in one launch (each CTA reduces
+// its 64 x 64 cells through six levels in shared memory, the last CTA to finish — ticket counter in the control block — the rest)
+bool publish_all_applicable(const Geom& g, int nlevels);
+cudaError_t launch_publish_all(const Geom& g, const Planes& p, int side, float* chain, uint32_t* flow, int nlevels, unsigned int* ticket,
+                               cudaStream_t st);
 // levels [first, last) of the chain at `base` (level L follows level L-1) in one single-CTA launch: the small tail
 cudaError_t launch_mip_tail(float* base, int W, int H, int first, int last, cudaStream_t st);
 cudaError_t launch_boundary_outflow(const Geom& g, const Planes& p, int side, double* out, cudaStream_t st);

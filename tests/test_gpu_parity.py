@@ -542,7 +542,7 @@ def test_step_host_band_pipeline_matches_oracle(tws, oracle_omp, W, H, name, bac
         assert_state_equal(sim, tws, t, f, v, f"{name} step_host without outputs")
 
 
-@pytest.mark.parametrize("W,H", [(1024, 1024), (300, 200), (37, 5), (5, 37), (257, 64), (1, 1)])
+@pytest.mark.parametrize("W,H", [(1024, 1024), (300, 200), (37, 5), (5, 37), (257, 64), (1, 1), (128, 128), (1024, 128), (256, 640), (2048, 1152)])
 def test_terrain_info_mip_chain_matches_oracle(tws, oracle, W, H):
     """Renderer hand-off: TerrainInfo level 0 = (terrain, 0.3, 0.3, water) and the mip chain the
     reference regenerates after every stepped frame (Terrain.cpp:272-276), against the pinned box filter of
@@ -561,6 +561,11 @@ def test_terrain_info_mip_chain_matches_oracle(tws, oracle, W, H):
         for l, (g_, w_) in enumerate(zip(got, want)):
             assert g_.shape == w_.shape, f"level {l}"
             assert np.array_equal(bits(g_), bits(w_)), f"level {l} differs"
+        # again (the single-pass kernel re-arms its ticket counter itself), after another step
+        sim.step(2)
+        oracle.step(t, f, v, c, 2)
+        for l, (g_, w_) in enumerate(zip(sim.publish_mips(), mip_chain(t))):
+            assert np.array_equal(bits(g_), bits(w_)), f"second publish: level {l} differs"
         # level 0 alone (tws_publish_packed) leaves the rest of the chain unpublished
         sim.step(1)
         sim.publish_packed()
