@@ -113,9 +113,9 @@ __device__ __forceinline__ void ledger_add(const StepConsts& c, const Geom& g, i
   }
   if (s != 0.0) atomicAdd(c.ledger, s * (double)c.area_inv);
 }
-// The same into a per-thread partial sum (flushed with ledger_src_flush at the end of the kernel): for the ring kernel, whose
-// static work split makes the launch as slow as its slowest column strip — an atomic per row of the two edge strips showed
-// up as 238 -> 185 Gcell/s at K = 3 (bisected, round 2).
+// The same into a per-thread partial sum (flushed with ledger_src_flush at the end of the kernel): for the ring kernel, where a
+// row of an edge column strip is the critical path of its ring turn — an atomic per row of the two edge strips showed up as
+// 238 -> 185 Gcell/s at K = 3 (bisected, round 2).
 __device__ __forceinline__ void ledger_acc(double& acc, const StepConsts& c, const Geom& g, int gx0, int gy, const float4& fx, const float4& fy,
                                            const float4& fz, const float4& fw) {
   const bool ytop = gy == 0, ybot = gy == g.Hg - 1;

@@ -24,6 +24,7 @@
 //   * No y-halo recomputation: each piece pays 2K warm-up rows once, and HBM sees 48/K B per
 //     cell-update plus the x-halo re-reads.
 #include "cell_math.cuh"
+#include "band_schedule.h"
 
 #include <cstdio>
 
@@ -272,11 +273,13 @@ __device__ __forceinline__ void stream_depth(const uint32_t up, const uint32_t d
 template <class C, bool EXT>
 __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_constant__ CUtensorMap tm_h,
                                                                const __grid_constant__ CUtensorMap tm_s,
+                                                               const __grid_constant__ BandSched sch,
                                                                FusedOut out, Geom g, StepConsts c, int lr0, int lr1, int nstrips,
-                                                               int tma_y_bias) {
+                                                               int tma_y_bias, uint32_t* sched) {
   constexpr int K = C::K, NW = C::NW, G = C::G, SXW = C::SXW, HX = C::HX, OX = C::OX, NHP = C::NHP, LAND = C::LAND;
   extern __shared__ __align__(1024) float smem[];
   __shared__ uint64_t full[NW];
+  __shared__ int next_piece[2];
   __shared__ __align__(16) uint64_t evt[NW][NHP][2];      // per slot, half-pass and ring-turn parity
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wup = (warp + NW - 1) % NW, wdn = (warp + 1) % NW;
@@ -301,17 +304,18 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
   uint32_t parity = 0;                                    // phase of this warp's landing barrier
   uint32_t turn_base = 0;                                 // ring turns completed by earlier pieces (event-barrier phases)
 
-  // This CTA's piece of the (strip, row) list: pieces are equal, contiguous, strip-major.
-  const long long R = (long long)(lr1 - lr0);
-  const long long TR = R * nstrips;
-  const long long lin_begin = TR * blockIdx.x / gridDim.x, lin_end = TR * (blockIdx.x + 1) / gridDim.x;
-
+  // Pieces (row segment x column strip) come from the same guided work list as the band kernel's (band_schedule.h): the CTA
+  // starts on the piece of its own index and then takes pieces from a device-wide counter, fetched one piece ahead and handed
+  // to the other warps through shared memory behind the block barriers between pieces.  Round 1 split the list into equal
+  // static shares: a launch then lasted as long as its slowest CTA — measured, the two edge column strips (masked scalar
+  // arithmetic, about 13/8 of the cost of an interior row) and the lake / shore regions (IEEE divisions) set the pace.
+  int piece = (int)blockIdx.x, pp = 0;
 #pragma unroll 1
-  for (long long lin = lin_begin; lin < lin_end;) {
-    const int strip = (int)(lin / R);
-    const int ya = lr0 + (int)(lin - (long long)strip * R);
-    const int yb = (int)((long long)ya + (lin_end - lin) < (long long)lr1 ? (long long)ya + (lin_end - lin) : (long long)lr1);
-    lin += yb - ya;
+  while (piece < sch.npieces) {
+    if (sched != nullptr && tid == 0) next_piece[pp] = (int)gridDim.x + (int)atomicAdd(sched, 1u);
+    int lev, strip, ya_rel, yb_rel;
+    band_decode(sch, piece, nstrips, lev, strip, ya_rel, yb_rel);
+    const int ya = lr0 + ya_rel, yb = lr0 + yb_rel;
     const int sx0 = strip * OX - HX;
     const int ystart = ya - 2 * K;                        // 2K warm-up rows above, 2K feeder rows below
     const int nrows = (yb - ya) + 4 * K;
@@ -420,6 +424,16 @@ __global__ void __launch_bounds__(C::NT, 1) stream_step_kernel(const __grid_cons
       }
     }
     turn_base += (uint32_t)turns;
+    __syncthreads();                                      // next_piece[pp] was written before the barriers at the top of this piece
+    piece = sched != nullptr ? next_piece[pp] : piece + (int)gridDim.x;
+    pp ^= 1;
+  }
+  // the last CTA to leave re-arms the counters for the next launch on this stream (every CTA that had a piece has by then seen
+  // its final, failing fetch)
+  if (sched != nullptr && (int)blockIdx.x < sch.npieces && tid == 0) {
+    const unsigned active = (unsigned)((int)gridDim.x < sch.npieces ? (int)gridDim.x : sch.npieces);
+    __threadfence();
+    if (atomicAdd(sched + 1, 1u) == active - 1u) { sched[0] = 0u; sched[1] = 0u; }
   }
   if (EXT) ledger_src_flush(c.ledger_src, src_acc);
   ledger_src_flush(c.ledger, out_acc);
@@ -446,7 +460,7 @@ static int stream_sm_count() {
 
 template <int K, bool EXT>
 static cudaError_t launch_stream_k(const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int lr0, int lr1,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, uint32_t* sched) {
   using C = typename StreamCfgFor<K>::type;
   static bool attr_set[64] = {};
   int dev = 0;
@@ -465,14 +479,12 @@ static cudaError_t launch_stream_k(const Geom& g, const Planes& p, const TmaSet&
   for (int i = 0; i < 4; ++i) out.F[i] = p.F[dst][i] + row0_off;
   out.v = p.v + row0_off;
   const int nstrips = (g.W + C::OX - 1) / C::OX;
-  const long long total_rows = (long long)nstrips * (lr1 - lr0);
-  // one persistent CTA per SM; small grids: at least ~4 ring turns of rows per CTA so the 4K warm-up rows amortise
-  const long long min_rows = 4 * C::NW;
-  long long want = (total_rows + min_rows - 1) / min_rows;
+  // one persistent CTA per SM (fewer when there are fewer pieces); a piece computes rows + 4K rows in whole ring turns
   const int sms = stream_sm_count();
-  const int grid = (int)(want < 1 ? 1 : (want < sms ? want : sms));
+  const BandSched sch = band_build_schedule(lr1 - lr0, nstrips, sms, C::NW, 2 * K, 0, 0, nullptr, nullptr, nullptr);
+  const int grid = sch.npieces < 1 ? 1 : (sch.npieces < sms ? sch.npieces : sms);
   const int bias = g.has_up ? TWS_HALO_ROWS : 0;
-  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], out, g, c, lr0, lr1, nstrips, bias);
+  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], sch, out, g, c, lr0, lr1, nstrips, bias, sched);
   return cudaGetLastError();
 }
 
@@ -482,10 +494,10 @@ cudaError_t launch_stream(int K, const Geom& g, const Planes& p, const TmaSet& t
   const bool ext = c.ext_sources != 0;
   if (impl == 1) return launch_band(K, g, p, tma, src, c, lr0, lr1, st, sched, cta_budget);
   switch (K) {
-    case 1: return ext ? launch_stream_k<1, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<1, false>(g, p, tma, src, c, lr0, lr1, st);
-    case 2: return ext ? launch_stream_k<2, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<2, false>(g, p, tma, src, c, lr0, lr1, st);
-    case 3: return ext ? launch_stream_k<3, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<3, false>(g, p, tma, src, c, lr0, lr1, st);
-    case 4: return ext ? launch_stream_k<4, true>(g, p, tma, src, c, lr0, lr1, st) : launch_stream_k<4, false>(g, p, tma, src, c, lr0, lr1, st);
+    case 1: return ext ? launch_stream_k<1, true>(g, p, tma, src, c, lr0, lr1, st, sched) : launch_stream_k<1, false>(g, p, tma, src, c, lr0, lr1, st, sched);
+    case 2: return ext ? launch_stream_k<2, true>(g, p, tma, src, c, lr0, lr1, st, sched) : launch_stream_k<2, false>(g, p, tma, src, c, lr0, lr1, st, sched);
+    case 3: return ext ? launch_stream_k<3, true>(g, p, tma, src, c, lr0, lr1, st, sched) : launch_stream_k<3, false>(g, p, tma, src, c, lr0, lr1, st, sched);
+    case 4: return ext ? launch_stream_k<4, true>(g, p, tma, src, c, lr0, lr1, st, sched) : launch_stream_k<4, false>(g, p, tma, src, c, lr0, lr1, st, sched);
     default: return cudaErrorInvalidValue;
   }
 }
