@@ -57,9 +57,14 @@ typedef enum tws_backend {
   TWS_BACKEND_STREAM_TB = 4,/* fused + temporal blocking as a row-streaming pipeline: one warp
                                per grid row, rows skewed in time instead of recomputed,
                                `temporal_block` steps per HBM round trip                  */
-  TWS_BACKEND_BAND_TB = 5   /* the same skewed row streaming run in lock step: bands of rows,
+  TWS_BACKEND_BAND_TB = 5,  /* the same skewed row streaming run in lock step: bands of rows,
                                one group barrier per half-pass instead of per-row barriers,
                                dynamic piece schedule, strip exchange fused into the launch */
+  TWS_BACKEND_RESIDENT = 6  /* grids that fit in the shared memory of the SMs (up to ~1 M cells: the
+                               reference's 1024 x 1024): ALL n steps of a tws_step / tws_advance call
+                               in one cooperative launch, one block of the grid resident per SM, rims
+                               exchanged neighbour to neighbour through L2.  Whole grids only;
+                               tws_create returns TWS_ERR_UNSUPPORTED for larger grids and strips */
 } tws_backend;
 
 typedef enum tws_boundary {

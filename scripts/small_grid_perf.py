@@ -7,8 +7,12 @@ import sys, time; sys.path.insert(0, '.')
 import ctypes as C
 import terrainwatersim_b200 as tws
 
-for W in (256, 1024, 2048):
-    for name, b, k in (("unfused", 1, 1), ("tile k=1", 2, 1), ("tile k=2", 3, 2), ("tile k=3", 3, 3), ("band k=2", 5, 2), ("band k=4", 5, 4)):
+only = sys.argv[1].split(',') if len(sys.argv) > 1 else None
+for W in (256, 512, 1024, 2048):
+    for name, b, k in (("unfused", 1, 1), ("tile k=1", 2, 1), ("tile k=2", 3, 2), ("tile k=3", 3, 3), ("band k=2", 5, 2), ("band k=4", 5, 4),
+                       ("resident", 6, 1)):
+        if (b == 6 and W > 1024) or (only and name.split()[0] not in only):
+            continue
         with tws.Terrain(W, backend=b, temporal_block=k) as sim:
             sim.CreateHeightmapFromNoiseAndResetSim()
             for _ in range(20): sim.step(10)
@@ -20,7 +24,9 @@ for W in (256, 1024, 2048):
             print(f"small {W:5d} {name:10s} graphs={sim.graph_replays() > 0} {dt / frames * 1e6:8.1f} us/frame(10 steps) wall, {gpu_us:7.1f} us on the device, {W * W * 10 * frames / dt / 1e9:8.2f} Gcell/s launches={sim.kernel_launches()}", flush=True)
 
 # the reference's frame: ApplyRadialWaterBrush + PerformSimulationStep(1/60 s) (one step) + GenMipMaps
-for name, b, k in (("unfused", 1, 1), ("fused", 2, 1), ("band k=1", 5, 1)):
+for name, b, k in (("unfused", 1, 1), ("fused", 2, 1), ("band k=1", 5, 1), ("resident", 6, 1)):
+    if only and name.split()[0] not in only:
+        continue
     with tws.Terrain(1024, backend=b, temporal_block=k) as sim:
         sim.CreateHeightmapFromNoiseAndResetSim()
         lib, h = sim._lib, sim._sim

@@ -23,6 +23,7 @@ BACKEND_FUSED = 2
 BACKEND_FUSED_TB = 3
 BACKEND_STREAM_TB = 4
 BACKEND_BAND_TB = 5
+BACKEND_RESIDENT = 6
 
 BOUNDARY_REFERENCE_OPEN = 0
 BOUNDARY_CLOSED = 1

@@ -13,7 +13,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libtws.so"
-SOURCES = ["tws_api.cu", "step_kernels.cu", "stream_kernels.cu", "band_kernels.cu", "aux_kernels.cu"]
+SOURCES = ["tws_api.cu", "step_kernels.cu", "stream_kernels.cu", "band_kernels.cu", "resident_kernels.cu", "aux_kernels.cu"]
 HEADERS = [CSRC / "tws_internal.h", CSRC / "cell_math.cuh", CSRC / "band_schedule.h", PKG_DIR.parent / "include" / "tws.h"]
 
 NVCC_FLAGS = [

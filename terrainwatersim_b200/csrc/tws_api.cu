@@ -62,6 +62,8 @@ struct tws_sim {
   bool timed = false;
   uint64_t launches = 0;
   uint32_t epoch = 0;                // exchange blocks completed (same on all strips)
+  int res_cfg = -1;                  // resident backend: block shape
+  uint32_t res_epoch = 0;            // resident backend: steps run so far (the blocks' flags count them)
   Peer up, down;
   bool connected = false;
   float* white_dev = nullptr;        // 4096-entry noise table
@@ -321,6 +323,14 @@ tws_status run_block(tws_sim* s, int k) {
     return TWS_OK;
   }
   if (is_stream_backend(s->prm.backend)) return run_block_stream(s, k);
+  if (s->prm.backend == TWS_BACKEND_RESIDENT) {           // k: any number of steps, one launch
+    TWS_CUDA(s, launch_resident(s->res_cfg, g, s->planes, s->consts, src, k, (uint32_t*)s->ctrl->res_flag, s->res_epoch, &s->ctrl->error,
+                                s->st_main));
+    s->res_epoch += (uint32_t)k;
+    s->launches += 1;
+    s->cur = (src + k) & 1;
+    return TWS_OK;
+  }
   tws_status r = ensure_tma(s, k);
   if (r) return r;
   const int tiles = fused_tile_rows(k, g.rows);
@@ -425,8 +435,9 @@ tws_status run_steps(tws_sim* s, int n) {
   if (strip && !s->connected) return fail(s, TWS_ERR_STATE, "strip sim stepped before tws_halo_connect");
   next_timing_pair(s);
   TWS_CUDA(s, cudaEventRecord(s->ev_start, s->st_main));
-  const int K = (s->prm.backend == TWS_BACKEND_FUSED_TB || is_stream_backend(s->prm.backend)) ? s->K : 1;
-  if (!strip && s->use_graphs && n >= 2 && n <= 64) {
+  const int K = s->prm.backend == TWS_BACKEND_RESIDENT ? (1 << 20)
+              : (s->prm.backend == TWS_BACKEND_FUSED_TB || is_stream_backend(s->prm.backend)) ? s->K : 1;
+  if (!strip && s->use_graphs && n >= 2 && n <= 64 && s->prm.backend != TWS_BACKEND_RESIDENT) {
     bool done = false;
     tws_status r = run_batch_graph(s, n, K, &done);
     if (r) return r;
@@ -449,7 +460,7 @@ tws_status sync_all(tws_sim* s) {
   TWS_CUDA(s, cudaStreamSynchronize(s->st_main));
   uint32_t e = 0;
   TWS_CUDA(s, cudaMemcpy(&e, &s->ctrl->error, sizeof(e), cudaMemcpyDeviceToHost));
-  if (e) return fail(s, TWS_ERR_STATE, "halo exchange timed out waiting for a neighbouring strip");
+  if (e) return fail(s, TWS_ERR_STATE, "halo exchange timed out waiting for a neighbouring strip (or, resident backend, a neighbouring block)");
   return TWS_OK;
 }
 
@@ -498,7 +509,9 @@ tws_status tws_create(const tws_params* p, tws_sim** out) {
   if (bad_float(p->flow_acceleration) || p->flow_acceleration < 0.0f) return fail(nullptr, TWS_ERR_INVALID, "tws_create: flow_acceleration must be >= 0");
   if (bad_float(p->rain_rate) || bad_float(p->evaporation_rate) || p->rain_rate < 0.0f || p->evaporation_rate < 0.0f)
     return fail(nullptr, TWS_ERR_INVALID, "tws_create: rain/evaporation must be >= 0");
-  if (p->backend < TWS_BACKEND_AUTO || p->backend > TWS_BACKEND_BAND_TB) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown backend");
+  if (p->backend < TWS_BACKEND_AUTO || p->backend > TWS_BACKEND_RESIDENT) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown backend");
+  if (strip && p->backend == TWS_BACKEND_RESIDENT)
+    return fail(nullptr, TWS_ERR_UNSUPPORTED, "tws_create: the resident backend runs whole grids only");
   if (p->boundary != TWS_BOUNDARY_REFERENCE_OPEN && p->boundary != TWS_BOUNDARY_CLOSED) return fail(nullptr, TWS_ERR_INVALID, "tws_create: unknown boundary");
   if ((p->backend == TWS_BACKEND_FUSED_TB || is_stream_backend(p->backend)) && (p->temporal_block < 1 || p->temporal_block > TWS_MAX_TB))
     return fail(nullptr, TWS_ERR_INVALID, "tws_create: temporal_block must be 1..4");
@@ -533,6 +546,14 @@ tws_status tws_create(const tws_params* p, tws_sim** out) {
   g.pitch = pitch_for(p->width);
   g.has_up = p->row_begin > 0; g.has_down = p->row_end < p->height;
   derive_constants(s);
+  if (p->backend == TWS_BACKEND_RESIDENT) {
+    s->res_cfg = resident_config(g);
+    if (s->res_cfg < 0 || resident_blocks(g, s->res_cfg) > (int)(sizeof(Control::res_flag) / sizeof(uint32_t))) {
+      g_create_error = "tws_create: the grid does not fit in the SMs' shared memory (resident backend: up to ~1 M cells)";
+      delete s;
+      return TWS_ERR_UNSUPPORTED;
+    }
+  }
   layout_planes(nullptr, g.pitch, g.rows, &s->planes, &s->plane_elems, &s->slab_bytes);
   tws_status rc = TWS_OK;
   auto bail = [&](tws_status code, const std::string& msg) { g_create_error = msg; tws_destroy(s); return code; };

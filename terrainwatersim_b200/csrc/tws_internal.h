@@ -47,6 +47,8 @@ struct Control {
   // a ledger that is to close has to book what the arithmetic did.
   alignas(128) double source_acc;
   alignas(128) uint32_t mip_ticket;  // CTAs of the mip chain's single-pass kernel that have finished (re-armed by the last one)
+  // Resident kernel: flag of block b = number of steps (over all launches of this sim) whose rim block b has published.
+  alignas(128) uint32_t res_flag[256];
 };
 
 static_assert(sizeof(Control) <= TWS_CTRL_BYTES, "the control block must fit in front of the planes");
@@ -131,6 +133,13 @@ cudaError_t launch_band(int K, const Geom& g, const Planes& p, const TmaSet& tma
 int stream_strip_width();
 cudaError_t launch_unfused_update(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st);
 cudaError_t launch_unfused_apply(const Geom& g, const Planes& p, int side, const StepConsts& c, int lr0, int lr1, cudaStream_t st);
+
+// Resident kernel (resident_kernels.cu): n steps of a whole grid that fits on chip in one cooperative launch.
+// resident_config: block shape index for this grid, -1 if it does not fit (or is a strip).
+int resident_config(const Geom& g);
+int resident_blocks(const Geom& g, int cfg);
+cudaError_t launch_resident(int cfg, const Geom& g, const Planes& p, const StepConsts& c, int src, int n, uint32_t* flags,
+                            uint32_t epoch0, uint32_t* error, cudaStream_t st);
 
 // ---- launchers (aux_kernels.cu) -------------------------------------------------------
 cudaError_t launch_brush(const Geom& g, float* d, float cx, float cy, float intensity, float size_sq, cudaStream_t st, int* launched);
