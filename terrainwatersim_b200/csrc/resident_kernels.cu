@@ -4,20 +4,20 @@
 // The six state planes of a 1024^2 grid are 25 MB; the 148 SMs of a B200 hold 33 MB of shared memory.  So the grid is cut
 // into one OX x OY block per SM (1024^2: 4 x 37 blocks of 256 x 28 cells), every CTA keeps its block — terrain, depth and
 // the four outflow planes, plus a halo of 2 rows / 4 columns — in shared memory for ALL n steps of the frame, and per step
-// only the block's rim goes through L2: after a step a CTA stores the depth of its outer two rings and the outflow of its
-// outer ring into the ping-pong planes in HBM/L2 (where the other kernels expect the state anyway), raises its flag, and
-// its eight neighbours pick their halo cells up from there.  The launch is cooperative (all CTAs are resident by
-// construction), the synchronisation is neighbour-to-neighbour (acquire / release flags in the control block), there is no
-// grid-wide barrier.
+// only the block's rim goes through L2, neighbour to neighbour; there is no grid-wide barrier and no flag: every value a
+// CTA publishes travels in an 8-byte word together with the number of the step it belongs to (the scheme NCCL calls LL),
+// so a reader polls the data itself and one L2 round trip is the whole hand-off.  (Round 2 first had the rims go through
+// the state planes behind acquire / release flags: publish -> fence -> flag -> poll -> fetch took 4.6 us per step and set the
+// step time on every grid size; %globaltimer traces in DESIGN.md section 8.)  The launch is cooperative: all CTAs are
+// resident by construction, which the polling relies on.
 //
-// A step's passes are ordered so that the exchange overlaps the arithmetic that does not depend on it.  The compute warps run
-//     depth(rim), publishing it -> A -> depth(interior) -> C -> flux(interior) of the NEXT step -> B -> flux(rim + halo ring) -> C
-// while a few extra warps do the exchange between A and B: raise the block's flag, wait for the eight neighbours' flags,
-// fetch the halo cells with cp.async (L2 -> shared memory, no registers; the addresses are per-thread constants).  A, B, C
-// are named barriers (A, B: everybody; C: the compute warps).  Measured with %globaltimer stamps (round 2): with one
-// exchange warp and the whole rim in the late pass, the chain publish -> flag -> poll -> fetch -> flux(late) -> depth(rim)
-// of 7 us, not the arithmetic (5.6 us), set the step time at 1024^2.  The halo ring's outflow is recomputed locally from its exchanged old
-// outflow and depth (the same redundant-halo scheme as the tile kernel, one cell deep), so one exchange per step suffices.
+// A step's passes are ordered so that the exchange overlaps the arithmetic that does not depend on it:
+//     depth(rim), publishing it -> depth(interior) -> issue the loads of the neighbours' rims -> | -> flux(early) of the NEXT
+//     step -> check the tags of what arrived (re-poll the words that are not there yet), halo -> shared memory -> |
+//     -> flux(late) -> |                                                                         ('|' = block barrier)
+// "early" are the items whose outflow needs no halo cell (all but the block's outermost row / group on each side), "late"
+// the outermost own items and the halo ring, whose outflow is recomputed locally from its exchanged old outflow and depth
+// (the same redundant-halo scheme as the tile kernel, one cell deep), so one exchange per step suffices.
 //
 // Arithmetic: the same cell functions as every other kernel (cell_math.cuh; flowUpdate.comp:34-59, flowApply.comp:32-46),
 // bit-identical to the oracle.  Exterior cells are zeros in shared memory (the reference's out-of-range imageLoad) and are
@@ -30,7 +30,7 @@ namespace tws {
 
 namespace {
 
-template <int OX_, int OY_, int NT_, int NX_>
+template <int OX_, int OY_, int NT_>
 struct ResCfg {
   static constexpr int OX = OX_, OY = OY_, NT = NT_;
   static constexpr int HX = 4, HY = 2;                       // halo: one float4 group / two rows on each side
@@ -38,7 +38,6 @@ struct ResCfg {
   static constexpr int NG = SX / 4;                          // float4 groups ("items") per staged row
   static constexpr int PLANE = SX * SY;                      // floats per plane
   static constexpr size_t SMEM = (size_t)6 * PLANE * sizeof(float);   // h, d, F x4
-  static constexpr int NX = NX_;                             // threads of the exchange warps
   // item sets, as (row, group) rectangles of the staged block:
   //   interior  own items that neither a neighbour nor the halo touches: rows [4, SY-4) x groups [2, NG-2)
   //   rim       the other own items: the outer two rows and the outer group on each side (what the neighbours read)
@@ -49,14 +48,20 @@ struct ResCfg {
   // outermost own items and the ring ("late") after it.
   static constexpr int IN_ROWS = SY - 8, IN_COLS = NG - 4, N_IN = IN_ROWS * IN_COLS;
   static constexpr int RIM_W = NG - 2, N_RIM = 4 * RIM_W + 2 * IN_ROWS;
-  static constexpr int N_EARLY = (IN_ROWS + 2) * IN_COLS;
   static constexpr int N_RING = 2 * NG + 2 * (SY - 4);
   static constexpr int N_OUTER = 2 * RIM_W + 2 * (IN_ROWS + 2);   // rows 2 and SY-3, groups 1 and NG-2 of rows [3, SY-3)
-  static constexpr int N_LATE = N_OUTER + N_RING;
   static constexpr int N_FAR = 2 * NG;
-  static constexpr int N_HALO = N_RING + N_FAR;
+  // early items beyond a whole number of rounds of the NT threads join the late pass when it has idle threads for them
+  static constexpr int N_EARLY_ALL = (IN_ROWS + 2) * IN_COLS;
+  static constexpr int EARLY_REM = N_EARLY_ALL % NT;
+  static constexpr bool MOVE_REM = N_EARLY_ALL > NT && EARLY_REM > 0 && (N_OUTER + N_RING) % NT != 0 &&
+                                   (N_OUTER + N_RING) % NT + EARLY_REM <= NT;
+  static constexpr int N_EARLY = MOVE_REM ? N_EARLY_ALL - EARLY_REM : N_EARLY_ALL;
+  static constexpr int N_LATE = N_OUTER + N_RING + (N_EARLY_ALL - N_EARLY);
+  // halo fetch: 16-byte words {value, tag, value, tag} — ring items have 5 planes x 2 words, far items (depth only) 2 words
+  static constexpr int N_WORDS = N_RING * 10 + N_FAR * 2;
   static constexpr int IPT_IN = (N_IN + NT - 1) / NT, IPT_EARLY = (N_EARLY + NT - 1) / NT, IPT_LATE = (N_LATE + NT - 1) / NT,
-                       IPT_RIM = (N_RIM + NT - 1) / NT, IPT_HALO = (N_HALO + NX - 1) / NX;
+                       IPT_RIM = (N_RIM + NT - 1) / NT, WPT = (N_WORDS + NT - 1) / NT;
   static_assert(OX % 4 == 0 && OY >= 4 && OX >= 16, "block too small for the interior / rim split");
   static_assert(PLANE < (1 << 16), "item descriptors keep the plane offset in 16 bits");
 };
@@ -76,20 +81,26 @@ struct ResPlanes {                 // plane pointers at LOCAL row 0
   uint32_t* v;
 };
 
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+// Mailbox: for every cell of the grid, plane p in {depth, F+X, F-X, F+Y, F-Y} and step parity q an 8-byte word
+// {fp32 value, step tag}; word index ((q * 5 + p) * cells + gy * pitch + gx).  Only rim cells are ever written.
+struct ResMail {
+  unsigned long long* base;
+  unsigned long long plane_words;    // pitch * Hg
+};
+__device__ __forceinline__ unsigned long long mail_word(float v, uint32_t tag) {
+  return ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
 }
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// two words per access: each 8-byte element is single-copy atomic, which is all the protocol needs
+__device__ __forceinline__ void mail_store2(unsigned long long* p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {     // L2 -> shared memory, bypassing L1
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+__device__ __forceinline__ void mail_load2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-template <int ID, int COUNT> __device__ __forceinline__ void bar_named() {
-  asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+__device__ __forceinline__ void mail_publish4(const ResMail& M, int q, int p, size_t go, const float4& v, uint32_t tag) {
+  unsigned long long* w = M.base + (size_t)(q * 5 + p) * M.plane_words + go;
+  mail_store2(w, mail_word(v.x, tag), mail_word(v.y, tag));
+  mail_store2(w + 2, mail_word(v.z, tag), mail_word(v.w, tag));
 }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void stcg4(float* p, const float4& v) { __stcg(reinterpret_cast<float4*>(p), v); }
@@ -192,11 +203,12 @@ __device__ __forceinline__ void res_flux_item(float* __restrict__ st, const int 
 }
 
 // ---- flowApply.comp for one own item --------------------------------------------------------------------------------
-// PUBLISH: the item is part of the rim — its new depth (and, outer ring, its outflow) also goes to side `pub` of the planes
-// in HBM/L2 for the neighbours.  LAST: the frame's final step — depth, outflow and the flow vector go to HBM.
+// PUBLISH: the item is part of the rim — its new depth (and, outermost ring, its outflow) also goes into the mailbox for the
+// neighbours, tagged with the step.  LAST: the frame's final step — depth, outflow and the flow vector go to the planes.
 template <class C, bool PUBLISH, bool LAST>
 __device__ __forceinline__ void res_depth_item(float* __restrict__ st, const int desc, const int gx_base, const int gy_base,
-                                               const Geom& g, const StepConsts& c, const ResPlanes& P, const int side, double& src_acc) {
+                                               const Geom& g, const StepConsts& c, const ResPlanes& P, const int side, const ResMail& M,
+                                               const uint32_t tag, double& src_acc) {
   constexpr int SX = C::SX, PLANE = C::PLANE;
   const int cls = (desc >> 16) & 3;
   if (cls == kClsSkip) return;
@@ -230,29 +242,34 @@ __device__ __forceinline__ void res_depth_item(float* __restrict__ st, const int
   }
   if (c.ledger_src != nullptr) src_acc += ((double)ds.x + (double)ds.y) + ((double)ds.z + (double)ds.w);
   if (!LAST) st4(sd + o, nd);
-  if (PUBLISH || LAST) {
-    const size_t go = (size_t)gy * (size_t)g.pitch + (size_t)gx0;
-    stcg4(P.d[side] + go, nd);
-    if (LAST || (desc & kFlagOuter)) {
-      stcg4(P.F[side][0] + go, fx); stcg4(P.F[side][1] + go, fy); stcg4(P.F[side][2] + go, fz); stcg4(P.F[side][3] + go, fw);
+  const size_t go = (size_t)gy * (size_t)g.pitch + (size_t)gx0;
+  if (PUBLISH) {
+    const int q = (int)(tag & 1u);
+    mail_publish4(M, q, 0, go, nd, tag);
+    if (desc & kFlagOuter) {
+      mail_publish4(M, q, 1, go, fx, tag); mail_publish4(M, q, 2, go, fy, tag);
+      mail_publish4(M, q, 3, go, fz, tag); mail_publish4(M, q, 4, go, fw, tag);
     }
-    if (LAST) *reinterpret_cast<uint4*>(P.v + go) = nv;
+  }
+  if (LAST) {
+    stcg4(P.d[side] + go, nd);
+    stcg4(P.F[side][0] + go, fx); stcg4(P.F[side][1] + go, fy); stcg4(P.F[side][2] + go, fz); stcg4(P.F[side][3] + go, fw);
+    *reinterpret_cast<uint4*>(P.v + go) = nv;
   }
 }
 
-// n steps of the whole grid; state side `src` -> side (src + n) & 1.  NT compute threads + NX exchange threads.
+// n steps of the whole grid; state side `src` -> side (src + n) & 1.  Steps are numbered epoch0 + 1 ... epoch0 + n (the tags).
 template <class C>
-__global__ void __launch_bounds__(C::NT + C::NX, 1) resident_step_kernel(ResPlanes P, Geom g, StepConsts c, int nbx, int nby, int src, int n,
-                                                                         uint32_t* flags, uint32_t epoch0, uint32_t* error) {
-  constexpr int SY = C::SY, NG = C::NG, PLANE = C::PLANE, NT = C::NT, NX = C::NX, NALL = C::NT + C::NX;
-  constexpr int BAR_C = 1, BAR_A = 2, BAR_B = 3, BAR_X = 4;
+__global__ void __launch_bounds__(C::NT, 1) resident_step_kernel(ResPlanes P, ResMail M, Geom g, StepConsts c, int nbx, int src, int n,
+                                                                 uint32_t epoch0, uint32_t* error) {
+  constexpr int SY = C::SY, NG = C::NG, PLANE = C::PLANE, NT = C::NT, WPT = C::WPT;
   extern __shared__ __align__(1024) float st[];
   const int tid = threadIdx.x;
   const int by = (int)blockIdx.x / nbx, bx = (int)blockIdx.x - by * nbx;
   const int gx_base = bx * C::OX - C::HX, gy_base = by * C::OY - C::HY;
 
   // ---- load the staged block (own cells + halo) from side src; exterior cells are zeros --------------------------------
-  for (int a = tid; a < NG * SY; a += NALL) {
+  for (int a = tid; a < NG * SY; a += NT) {
     const int r = a / NG, gc = a - r * NG;
     const int gy = gy_base + r, gx0 = gx_base + 4 * gc;
     const bool in = (unsigned)gy < (unsigned)g.Hg && (unsigned)gx0 < (unsigned)g.pitch;
@@ -264,61 +281,8 @@ __global__ void __launch_bounds__(C::NT + C::NX, 1) resident_step_kernel(ResPlan
 #pragma unroll
     for (int k = 0; k < 4; ++k) st4(st + (2 + k) * PLANE + o, in ? ldcg4(P.F[src][k] + go) : z);
   }
-  __syncthreads();
 
-  if (tid >= NT) {
-    // ---- the exchange warps ---------------------------------------------------------------------------------------------
-    const int xt = tid - NT;
-    int watch = -1;                                       // thread j < 8 watches neighbour j
-    if (xt < 8) {
-      const int dx = (xt == 0 || xt == 3 || xt == 5) ? -1 : ((xt == 2 || xt == 4 || xt == 7) ? 1 : 0);
-      const int dy = xt < 3 ? -1 : (xt < 5 ? 0 : 1);
-      const int qx = bx + dx, qy = by + dy;
-      if (qx >= 0 && qx < nbx && qy >= 0 && qy < nby) watch = qy * nbx + qx;
-    }
-    // this thread's halo items: shared-memory offset (negative: exterior or none, stays zero), plane offset, ring or far
-    int ho[C::IPT_HALO]; unsigned hg[C::IPT_HALO]; bool hring[C::IPT_HALO];
-#pragma unroll
-    for (int q = 0; q < C::IPT_HALO; ++q) {
-      const int i = xt + q * NX;
-      int r = 0, gc = 0;
-      hring[q] = i < C::N_RING;
-      if (hring[q]) pos_ring<C>(i, r, gc); else if (i < C::N_HALO) pos_far<C>(i - C::N_RING, r, gc);
-      const int gy = gy_base + r, gx0 = gx_base + 4 * gc;
-      const bool in = i < C::N_HALO && (unsigned)gy < (unsigned)g.Hg && (unsigned)gx0 < (unsigned)g.pitch;
-      ho[q] = in ? (r * NG + gc) * 4 : -1;
-      hg[q] = in ? (unsigned)gy * (unsigned)g.pitch + (unsigned)gx0 : 0u;
-    }
-    bool dead = false;                                    // a wait timed out: stop waiting, the host reports the error
-#pragma unroll 1
-    for (int t = 1; t < n; ++t) {
-      const int side = (src + t) & 1;
-      bar_named<BAR_A, NALL>();                           // the rim of step t is on its way to L2; the halo cells are free
-      if (xt == 0) st_release_u32(flags + blockIdx.x, epoch0 + (uint32_t)t);
-      if (watch >= 0 && !dead) {
-        const uint32_t want = epoch0 + (uint32_t)t;
-        uint32_t spins = 0;
-        while ((int32_t)(ld_acquire_u32(flags + watch) - want) < 0) {
-          if (++spins > (1u << 22)) { dead = true; atomicExch(error, 1u); break; }
-        }
-      }
-      bar_named<BAR_X, NX>();                             // the neighbours' rims of step t are in L2
-#pragma unroll
-      for (int q = 0; q < C::IPT_HALO; ++q) {
-        if (ho[q] < 0) continue;
-        cp_async16(st + PLANE + ho[q], P.d[side] + hg[q]);
-        if (hring[q]) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) cp_async16(st + (2 + k) * PLANE + ho[q], P.F[side][k] + hg[q]);
-        }
-      }
-      cp_async_wait_all();
-      bar_named<BAR_B, NALL>();                           // the halo of step t + 1 is in shared memory
-    }
-    return;
-  }
-
-  // ---- the compute warps: this thread's items (the same every step) -----------------------------------------------------
+  // ---- this thread's items (the same every step) ------------------------------------------------------------------------
   int it_in[C::IPT_IN], it_early[C::IPT_EARLY], it_late[C::IPT_LATE], it_rim[C::IPT_RIM];
 #pragma unroll
   for (int q = 0; q < C::IPT_IN; ++q) {
@@ -334,10 +298,13 @@ __global__ void __launch_bounds__(C::NT + C::NX, 1) resident_step_kernel(ResPlan
   }
 #pragma unroll
   for (int q = 0; q < C::IPT_LATE; ++q) {
-    const int i = tid + q * NT;
+    int i = tid + q * NT;
     int r = 0, gc = 0;
-    if (i < C::N_OUTER) pos_outer<C>(i, r, gc); else if (i < C::N_LATE) pos_ring<C>(i - C::N_OUTER, r, gc);
-    it_late[q] = i < C::N_LATE ? describe<C>(r, gc, gx_base, gy_base, g, c) : 0;
+    const bool any = i < C::N_LATE;
+    if (i < C::N_OUTER) pos_outer<C>(i, r, gc);
+    else if (i < C::N_OUTER + C::N_RING) pos_ring<C>(i - C::N_OUTER, r, gc);
+    else if (any) pos_early<C>(C::N_EARLY + (i - C::N_OUTER - C::N_RING), r, gc);
+    it_late[q] = any ? describe<C>(r, gc, gx_base, gy_base, g, c) : 0;
   }
 #pragma unroll
   for (int q = 0; q < C::IPT_RIM; ++q) {
@@ -346,6 +313,20 @@ __global__ void __launch_bounds__(C::NT + C::NX, 1) resident_step_kernel(ResPlan
     if (i < C::N_RIM) pos_rim<C>(i, r, gc);
     it_rim[q] = i < C::N_RIM ? describe<C>(r, gc, gx_base, gy_base, g, c) : 0;
   }
+  // ... and the mailbox words it fetches: word offset within a parity's planes, shared-memory destination (< 0: none / exterior)
+  unsigned long long mw[WPT]; int mo[WPT];
+#pragma unroll
+  for (int q = 0; q < WPT; ++q) {
+    const int u = tid + q * NT;
+    int r = 0, gc = 0, p = 0, half = 0;
+    if (u < C::N_RING * 10) { const int it = u / 10, rem = u - it * 10; p = rem >> 1; half = rem & 1; pos_ring<C>(it, r, gc); }
+    else if (u < C::N_WORDS) { const int v = u - C::N_RING * 10; half = v & 1; pos_far<C>(v >> 1, r, gc); }
+    const int gy = gy_base + r, gx0 = gx_base + 4 * gc;
+    const bool in = u < C::N_WORDS && (unsigned)gy < (unsigned)g.Hg && gx0 >= 0 && gx0 < g.W;   // published by a neighbour (cf. describe)
+    mo[q] = in ? (1 + p) * PLANE + (r * NG + gc) * 4 + half * 2 : -1;
+    mw[q] = in ? (unsigned long long)p * M.plane_words + (unsigned long long)gy * (unsigned)g.pitch + (unsigned)(gx0 + half * 2) : 0ull;
+  }
+  __syncthreads();
 
   double out_acc = 0.0, src_acc = 0.0;
   // ---- step 1: outflow of everything ------------------------------------------------------------------------------------
@@ -353,32 +334,47 @@ __global__ void __launch_bounds__(C::NT + C::NX, 1) resident_step_kernel(ResPlan
   for (int q = 0; q < C::IPT_EARLY; ++q) res_flux_item<C>(st, it_early[q], gx_base, gy_base, g, c, out_acc);
 #pragma unroll
   for (int q = 0; q < C::IPT_LATE; ++q) res_flux_item<C>(st, it_late[q], gx_base, gy_base, g, c, out_acc);
-  bar_named<BAR_C, NT>();
+  __syncthreads();
 
+  bool dead = false;                                      // a poll timed out: stop waiting, the host reports the error
 #pragma unroll 1
   for (int t = 1; t <= n; ++t) {
     const int side = (src + t) & 1;                       // where the state after step t lives
+    const uint32_t tag = epoch0 + (uint32_t)t;
     if (t == n) {                                         // the frame's last step: everything goes to HBM
 #pragma unroll
-      for (int q = 0; q < C::IPT_RIM; ++q) res_depth_item<C, false, true>(st, it_rim[q], gx_base, gy_base, g, c, P, side, src_acc);
+      for (int q = 0; q < C::IPT_RIM; ++q) res_depth_item<C, false, true>(st, it_rim[q], gx_base, gy_base, g, c, P, side, M, tag, src_acc);
 #pragma unroll
-      for (int q = 0; q < C::IPT_IN; ++q) res_depth_item<C, false, true>(st, it_in[q], gx_base, gy_base, g, c, P, side, src_acc);
+      for (int q = 0; q < C::IPT_IN; ++q) res_depth_item<C, false, true>(st, it_in[q], gx_base, gy_base, g, c, P, side, M, tag, src_acc);
       break;
     }
     // rim first: the neighbours are waiting for it
 #pragma unroll
-    for (int q = 0; q < C::IPT_RIM; ++q) res_depth_item<C, true, false>(st, it_rim[q], gx_base, gy_base, g, c, P, side, src_acc);
-    bar_named<BAR_A, NALL>();
+    for (int q = 0; q < C::IPT_RIM; ++q) res_depth_item<C, true, false>(st, it_rim[q], gx_base, gy_base, g, c, P, side, M, tag, src_acc);
 #pragma unroll
-    for (int q = 0; q < C::IPT_IN; ++q) res_depth_item<C, false, false>(st, it_in[q], gx_base, gy_base, g, c, P, side, src_acc);
-    bar_named<BAR_C, NT>();                               // the block's depth of step t is complete
-    // step t + 1: the outflow of all but the outermost own items needs nothing from outside the block
+    for (int q = 0; q < C::IPT_IN; ++q) res_depth_item<C, false, false>(st, it_in[q], gx_base, gy_base, g, c, P, side, M, tag, src_acc);
+    // the neighbours' rims of step t: the loads fly while the early outflow of step t + 1 is computed
+    const unsigned long long* mbase = M.base + (size_t)(tag & 1u) * 5u * M.plane_words;
+    unsigned long long wa[WPT], wb[WPT];
+#pragma unroll
+    for (int q = 0; q < WPT; ++q) { wa[q] = 0ull; wb[q] = 0ull; if (mo[q] >= 0) mail_load2(mbase + mw[q], wa[q], wb[q]); }
+    __syncthreads();                                      // the block's depth of step t is complete
 #pragma unroll
     for (int q = 0; q < C::IPT_EARLY; ++q) res_flux_item<C>(st, it_early[q], gx_base, gy_base, g, c, out_acc);
-    bar_named<BAR_B, NALL>();
+#pragma unroll
+    for (int q = 0; q < WPT; ++q) {
+      if (mo[q] < 0) continue;
+      uint32_t spins = 0;
+      while (((uint32_t)(wa[q] >> 32) != tag || (uint32_t)(wb[q] >> 32) != tag) && !dead) {
+        mail_load2(mbase + mw[q], wa[q], wb[q]);
+        if (++spins > (1u << 21)) { dead = true; atomicExch(error, 1u); }
+      }
+      *reinterpret_cast<float2*>(st + mo[q]) = make_float2(__uint_as_float((uint32_t)wa[q]), __uint_as_float((uint32_t)wb[q]));
+    }
+    __syncthreads();                                      // the halo of step t + 1 is in shared memory
 #pragma unroll
     for (int q = 0; q < C::IPT_LATE; ++q) res_flux_item<C>(st, it_late[q], gx_base, gy_base, g, c, out_acc);
-    bar_named<BAR_C, NT>();
+    __syncthreads();
   }
   if (c.ledger_src != nullptr) ledger_src_flush(c.ledger_src, src_acc);
   ledger_src_flush(c.ledger, out_acc);
@@ -386,11 +382,10 @@ __global__ void __launch_bounds__(C::NT + C::NX, 1) resident_step_kernel(ResPlan
 
 // Block shapes: the widest one covers 1024^2 with one block per SM of a B200 (4 x 37 = 148); the smaller ones give small
 // grids more blocks (latency, not throughput, is what a 256^2 frame is bound by).
-// (threads: NT compute + NX exchange; 640 threads leave 96 registers per thread)
-using ResA = ResCfg<256, 28, 544, 96>;
-using ResB = ResCfg<128, 28, 512, 128>;
-using ResC = ResCfg<128, 12, 512, 128>;
-using ResD = ResCfg<64, 12, 256, 64>;
+using ResA = ResCfg<256, 28, 512>;
+using ResB = ResCfg<128, 28, 512>;
+using ResC = ResCfg<128, 12, 512>;
+using ResD = ResCfg<64, 12, 256>;
 
 int res_sm_count() {
   static int cached[64] = {};
@@ -408,7 +403,7 @@ bool res_fits(const Geom& g, int sms, long long* staged) {
 }
 
 template <class C>
-cudaError_t res_launch(const Geom& g, const Planes& p, const StepConsts& c, int src, int n, uint32_t* flags, uint32_t epoch0,
+cudaError_t res_launch(const Geom& g, const Planes& p, const StepConsts& c, int src, int n, void* mailbox, uint32_t epoch0,
                        uint32_t* error, cudaStream_t st) {
   static bool attr_set[64] = {};
   int dev = 0;
@@ -427,12 +422,15 @@ cudaError_t res_launch(const Geom& g, const Planes& p, const StepConsts& c, int 
     for (int i = 0; i < 4; ++i) P.F[s][i] = p.F[s][i] + row0_off;
   }
   P.v = p.v + row0_off;
+  ResMail M;
+  M.base = (unsigned long long*)mailbox;
+  M.plane_words = (unsigned long long)g.pitch * (unsigned long long)g.Hg;
   int nbx = (g.W + C::OX - 1) / C::OX, nby = (g.Hg + C::OY - 1) / C::OY;
   Geom gg = g;
   StepConsts cc = c;
-  void* args[] = {&P, &gg, &cc, &nbx, &nby, &src, &n, &flags, &epoch0, &error};
-  // cooperative: every CTA of the grid is resident before any of them runs, which the neighbour waits rely on
-  return cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)(nbx * nby)), dim3(C::NT + C::NX), args, C::SMEM, st);
+  void* args[] = {&P, &M, &gg, &cc, &nbx, &src, &n, &epoch0, &error};
+  // cooperative: every CTA of the grid is resident before any of them runs, which the polling of the neighbours relies on
+  return cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)(nbx * nby)), dim3(C::NT), args, C::SMEM, st);
 }
 
 }  // namespace
@@ -462,14 +460,16 @@ int resident_blocks(const Geom& g, int cfg) {
   }
 }
 
-cudaError_t launch_resident(int cfg, const Geom& g, const Planes& p, const StepConsts& c, int src, int n, uint32_t* flags,
+size_t resident_mailbox_bytes(const Geom& g) { return (size_t)10 * (size_t)g.pitch * (size_t)g.Hg * sizeof(unsigned long long); }
+
+cudaError_t launch_resident(int cfg, const Geom& g, const Planes& p, const StepConsts& c, int src, int n, void* mailbox,
                             uint32_t epoch0, uint32_t* error, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   switch (cfg) {
-    case 0: return res_launch<ResA>(g, p, c, src, n, flags, epoch0, error, st);
-    case 1: return res_launch<ResB>(g, p, c, src, n, flags, epoch0, error, st);
-    case 2: return res_launch<ResC>(g, p, c, src, n, flags, epoch0, error, st);
-    case 3: return res_launch<ResD>(g, p, c, src, n, flags, epoch0, error, st);
+    case 0: return res_launch<ResA>(g, p, c, src, n, mailbox, epoch0, error, st);
+    case 1: return res_launch<ResB>(g, p, c, src, n, mailbox, epoch0, error, st);
+    case 2: return res_launch<ResC>(g, p, c, src, n, mailbox, epoch0, error, st);
+    case 3: return res_launch<ResD>(g, p, c, src, n, mailbox, epoch0, error, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -63,7 +63,8 @@ struct tws_sim {
   uint64_t launches = 0;
   uint32_t epoch = 0;                // exchange blocks completed (same on all strips)
   int res_cfg = -1;                  // resident backend: block shape
-  uint32_t res_epoch = 0;            // resident backend: steps run so far (the blocks' flags count them)
+  uint32_t res_epoch = 0;            // resident backend: steps run so far (the tags of the rim exchange count them)
+  void* res_mailbox = nullptr;       // resident backend: the rim exchange's mailbox (device)
   Peer up, down;
   bool connected = false;
   float* white_dev = nullptr;        // 4096-entry noise table
@@ -324,8 +325,11 @@ tws_status run_block(tws_sim* s, int k) {
   }
   if (is_stream_backend(s->prm.backend)) return run_block_stream(s, k);
   if (s->prm.backend == TWS_BACKEND_RESIDENT) {           // k: any number of steps, one launch
-    TWS_CUDA(s, launch_resident(s->res_cfg, g, s->planes, s->consts, src, k, (uint32_t*)s->ctrl->res_flag, s->res_epoch, &s->ctrl->error,
-                                s->st_main));
+    if (!s->res_mailbox) {
+      TWS_CUDA(s, cudaMalloc(&s->res_mailbox, resident_mailbox_bytes(g)));
+      TWS_CUDA(s, cudaMemsetAsync(s->res_mailbox, 0, resident_mailbox_bytes(g), s->st_main));
+    }
+    TWS_CUDA(s, launch_resident(s->res_cfg, g, s->planes, s->consts, src, k, s->res_mailbox, s->res_epoch, &s->ctrl->error, s->st_main));
     s->res_epoch += (uint32_t)k;
     s->launches += 1;
     s->cur = (src + k) & 1;
@@ -548,7 +552,7 @@ tws_status tws_create(const tws_params* p, tws_sim** out) {
   derive_constants(s);
   if (p->backend == TWS_BACKEND_RESIDENT) {
     s->res_cfg = resident_config(g);
-    if (s->res_cfg < 0 || resident_blocks(g, s->res_cfg) > (int)(sizeof(Control::res_flag) / sizeof(uint32_t))) {
+    if (s->res_cfg < 0) {
       g_create_error = "tws_create: the grid does not fit in the SMs' shared memory (resident backend: up to ~1 M cells)";
       delete s;
       return TWS_ERR_UNSUPPORTED;
@@ -595,6 +599,7 @@ tws_status tws_destroy(tws_sim* s) {
   if (s->st_d2h) { cudaStreamSynchronize(s->st_d2h); cudaStreamDestroy(s->st_d2h); }
   if (s->staging) cudaFree(s->staging);
   if (s->partials) cudaFree(s->partials);
+  if (s->res_mailbox) cudaFree(s->res_mailbox);
   if (s->white_dev) cudaFree(s->white_dev);
   tws_gl_unregister(s);
   if (s->packed_info) cudaFree(s->packed_info);

@@ -47,8 +47,6 @@ struct Control {
   // a ledger that is to close has to book what the arithmetic did.
   alignas(128) double source_acc;
   alignas(128) uint32_t mip_ticket;  // CTAs of the mip chain's single-pass kernel that have finished (re-armed by the last one)
-  // Resident kernel: flag of block b = number of steps (over all launches of this sim) whose rim block b has published.
-  alignas(128) uint32_t res_flag[256];
 };
 
 static_assert(sizeof(Control) <= TWS_CTRL_BYTES, "the control block must fit in front of the planes");
@@ -138,7 +136,10 @@ cudaError_t launch_unfused_apply(const Geom& g, const Planes& p, int side, const
 // resident_config: block shape index for this grid, -1 if it does not fit (or is a strip).
 int resident_config(const Geom& g);
 int resident_blocks(const Geom& g, int cfg);
-cudaError_t launch_resident(int cfg, const Geom& g, const Planes& p, const StepConsts& c, int src, int n, uint32_t* flags,
+// mailbox: resident_mailbox_bytes(g) of zeroed device memory (the rims travel through it, tagged with their step number);
+// epoch0: steps this sim's resident launches have run before (tags must never repeat)
+size_t resident_mailbox_bytes(const Geom& g);
+cudaError_t launch_resident(int cfg, const Geom& g, const Planes& p, const StepConsts& c, int src, int n, void* mailbox,
                             uint32_t epoch0, uint32_t* error, cudaStream_t st);
 
 // ---- launchers (aux_kernels.cu) -------------------------------------------------------

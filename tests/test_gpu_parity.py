@@ -17,7 +17,8 @@ GOLD = json.loads((ROOT / "tests" / "golden" / "goldens.json").read_text())
 
 BACKENDS = [("unfused", 1, 1), ("fused", 2, 1), ("tb2", 3, 2), ("tb3", 3, 3), ("tb4", 3, 4),
             ("stream1", 4, 1), ("stream2", 4, 2), ("stream3", 4, 3), ("stream4", 4, 4),
-            ("band1", 5, 1), ("band2", 5, 2), ("band3", 5, 3), ("band4", 5, 4)]
+            ("band1", 5, 1), ("band2", 5, 2), ("band3", 5, 3), ("band4", 5, 4),
+            ("resident", 6, 1)]       # grids that fit on chip only: all n steps of a call in one launch
 
 
 def bits(a):
@@ -470,6 +471,8 @@ def test_8192_backends_bitwise_equal_and_oracle_few_steps(tws, oracle_omp):
     W = 8192
     ref = {}
     for name, backend, k in BACKENDS:
+        if backend == tws.BACKEND_RESIDENT:
+            continue                                   # 67 M cells do not fit in shared memory
         with make_sim(tws, W, W, backend, k) as sim:
             sim.CreateHeightmapFromNoiseAndResetSim()
             sim.inject_brush(4096.0, 4100.5, 25.0, 900.0)
@@ -505,12 +508,14 @@ def test_8192_closed_domain_conserves_volume(tws):
         assert abs(v1 - v0) / v0 < 1e-6
 
 
-@pytest.mark.parametrize("name,backend,k", [BACKENDS[0], BACKENDS[1], BACKENDS[2], BACKENDS[5], BACKENDS[8], BACKENDS[11]])
+@pytest.mark.parametrize("name,backend,k", [BACKENDS[0], BACKENDS[1], BACKENDS[2], BACKENDS[5], BACKENDS[8], BACKENDS[11], BACKENDS[13]])
 @pytest.mark.parametrize("W,H", [(2048, 3000), (250, 190), (37, 5), (1, 1), (4100, 1100)])
 def test_step_host_band_pipeline_matches_oracle(tws, oracle_omp, W, H, name, backend, k):
     """tws_step_host (band-pipelined upload / step / readback, several bands at 2048x3000 and
     4100x1100) against the oracle driven the same way: the host owns the water layer, edits it
     between steps, and gets depth + flow vector back each step."""
+    if backend == tws.BACKEND_RESIDENT and W * H > 1000 * 1000:
+        pytest.skip("does not fit on chip")
     h, d = bumpy(W, H, seed=11)
     c = oracle_omp.derive_consts(float(W), W)
     t, f, v = new_state(h, d)
@@ -588,6 +593,44 @@ def test_gl_interop_without_a_gl_context_fails_cleanly(tws):
         sim.gl_unregister(); sim.gl_unregister()
         sim.step(2)                                           # the sim is still usable
         assert np.isfinite(sim.total_volume())
+
+
+@pytest.mark.parametrize("W,H", [(1024, 1024), (1000, 1030), (1021, 700), (512, 512), (384, 900), (256, 256), (130, 29), (64, 12), (65, 13)])
+@pytest.mark.parametrize("boundary", ["open", "closed"])
+def test_resident_backend_frames_of_any_length_match_the_oracle(tws, oracle_omp, W, H, boundary):
+    """TWS_BACKEND_RESIDENT: every tws_step(n) is ONE launch that keeps the grid in shared memory for all n steps and
+    exchanges block rims through tagged words in L2.  Frames of 1, 2, 3, 10 and 25 steps back to back (the step tags run on
+    across launches), a brush between frames, every block shape (256x28, 128x28, 128x12, 64x12), ragged sizes, both
+    boundary modes, rain + evaporation with both ledgers."""
+    closed = boundary == "closed"
+    h, d = bumpy(W, H, seed=11)
+    rain, evap = 0.8, 0.3
+    dt = float(np.float32(1.0) / np.float32(60.0))
+    rs, es = float(np.float32(dt * np.float32(rain))), float(np.float32(dt * np.float32(evap)))
+    c = oracle_omp.derive_consts(float(W), W)
+    t, f, v = new_state(h, d)
+    with make_sim(tws, W, H, tws.BACKEND_RESIDENT, 1, boundary=tws.BOUNDARY_CLOSED if closed else tws.BOUNDARY_REFERENCE_OPEN,
+                  rain_rate=rain, evaporation_rate=evap) as sim:
+        assert sim.backend_in_use()[0] == tws.BACKEND_RESIDENT
+        sim.upload(tws.FIELD_TERRAIN, h)
+        sim.upload(tws.FIELD_WATER, d)
+        for n in (1, 2, 3, 10, 25):
+            sim.inject_brush(W * 0.5, H * 0.25, 0.75, 40.0)
+            oracle_omp.brush(t, W * 0.5, H * 0.25, 0.75, 40.0)
+            launches = sim.kernel_launches()
+            sim.step(n)
+            assert sim.kernel_launches() - launches == 1
+            oracle_omp.step(t, f, v, c, n, boundary=1 if closed else 0, rain_step=rs, evap_step=es)
+            assert_state_equal(sim, tws, t, f, v, f"resident {W}x{H} {boundary} after a frame of {n}")
+
+
+def test_resident_backend_refuses_what_does_not_fit(tws):
+    with pytest.raises(tws.TwsError) as e:
+        tws.Terrain(2048, backend=tws.BACKEND_RESIDENT)
+    assert e.value.status == -5                        # TWS_ERR_UNSUPPORTED
+    with pytest.raises(tws.TwsError) as e:
+        tws.Terrain(1024, rows=(0, 512), backend=tws.BACKEND_RESIDENT)
+    assert e.value.status == -5
 
 
 def test_auto_backend_resolves_by_grid_size_and_matches_the_oracle(tws, oracle):
