@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(C::NT, 1) resident_step_kernel(ResPlanes P, Re
   const int gx_base = bx * C::OX - C::HX, gy_base = by * C::OY - C::HY;
 
   // ---- load the staged block (own cells + halo) from side src; exterior cells are zeros --------------------------------
+#pragma unroll 2
   for (int a = tid; a < NG * SY; a += NT) {
     const int r = a / NG, gc = a - r * NG;
     const int gy = gy_base + r, gx0 = gx_base + 4 * gc;
@@ -382,10 +383,13 @@ __global__ void __launch_bounds__(C::NT, 1) resident_step_kernel(ResPlanes P, Re
 
 // Block shapes: the widest one covers 1024^2 with one block per SM of a B200 (4 x 37 = 148); the smaller ones give small
 // grids more blocks (latency, not throughput, is what a 256^2 frame is bound by).
-using ResA = ResCfg<256, 28, 512>;
+using ResA = ResCfg<256, 28, 512>;     // 1024^2: 4 x 37 = 148 blocks
 using ResB = ResCfg<128, 28, 512>;
-using ResC = ResCfg<128, 12, 512>;
-using ResD = ResCfg<64, 12, 256>;
+using ResC = ResCfg<128, 14, 512>;     //  512^2: 4 x 37
+using ResD = ResCfg<128, 12, 512>;
+using ResE = ResCfg<64, 12, 256>;
+using ResF = ResCfg<64, 8, 256>;       //  256^2: 4 x 32
+#define TWS_RES_CONFIGS(X) X(0, ResA) X(1, ResB) X(2, ResC) X(3, ResD) X(4, ResE) X(5, ResF)
 
 int res_sm_count() {
   static int cached[64] = {};
@@ -442,20 +446,18 @@ int resident_config(const Geom& g) {
   const int sms = res_sm_count();
   long long best = -1, s = 0;
   int cfg = -1;
-  if (res_fits<ResA>(g, sms, &s) && (best < 0 || s < best)) { best = s; cfg = 0; }
-  if (res_fits<ResB>(g, sms, &s) && (best < 0 || s < best)) { best = s; cfg = 1; }
-  if (res_fits<ResC>(g, sms, &s) && (best < 0 || s < best)) { best = s; cfg = 2; }
-  if (res_fits<ResD>(g, sms, &s) && (best < 0 || s < best)) { best = s; cfg = 3; }
+#define X(I, C) if (res_fits<C>(g, sms, &s) && (best < 0 || s < best)) { best = s; cfg = I; }
+  TWS_RES_CONFIGS(X)
+#undef X
   return cfg;
 }
 
 int resident_blocks(const Geom& g, int cfg) {
   auto nb = [&](int ox, int oy) { return ((g.W + ox - 1) / ox) * ((g.Hg + oy - 1) / oy); };
   switch (cfg) {
-    case 0: return nb(ResA::OX, ResA::OY);
-    case 1: return nb(ResB::OX, ResB::OY);
-    case 2: return nb(ResC::OX, ResC::OY);
-    case 3: return nb(ResD::OX, ResD::OY);
+#define X(I, C) case I: return nb(C::OX, C::OY);
+    TWS_RES_CONFIGS(X)
+#undef X
     default: return 0;
   }
 }
@@ -466,10 +468,9 @@ cudaError_t launch_resident(int cfg, const Geom& g, const Planes& p, const StepC
                             uint32_t epoch0, uint32_t* error, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   switch (cfg) {
-    case 0: return res_launch<ResA>(g, p, c, src, n, mailbox, epoch0, error, st);
-    case 1: return res_launch<ResB>(g, p, c, src, n, mailbox, epoch0, error, st);
-    case 2: return res_launch<ResC>(g, p, c, src, n, mailbox, epoch0, error, st);
-    case 3: return res_launch<ResD>(g, p, c, src, n, mailbox, epoch0, error, st);
+#define X(I, C) case I: return res_launch<C>(g, p, c, src, n, mailbox, epoch0, error, st);
+    TWS_RES_CONFIGS(X)
+#undef X
     default: return cudaErrorInvalidValue;
   }
 }

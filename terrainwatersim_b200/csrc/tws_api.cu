@@ -63,6 +63,8 @@ struct tws_sim {
   uint64_t launches = 0;
   uint32_t epoch = 0;                // exchange blocks completed (same on all strips)
   int res_cfg = -1;                  // resident backend: block shape
+  bool auto_picked = false;          // the backend was chosen by TWS_BACKEND_AUTO
+  bool res_auto = false;             // TWS_BACKEND_AUTO on a grid that fits on chip: frames of >= kResidentMinSteps steps go resident
   uint32_t res_epoch = 0;            // resident backend: steps run so far (the tags of the rim exchange count them)
   void* res_mailbox = nullptr;       // resident backend: the rim exchange's mailbox (device)
   Peer up, down;
@@ -433,6 +435,11 @@ void next_timing_pair(tws_sim* s) {
   s->batches_timed += 1;
 }
 
+// Measured (scripts/resident_perf.py, profiles/r02_resident_frames.log): from 4 steps per call on, one resident launch beats
+// the captured batch of tile-kernel launches on grids that fill the SMs (1024^2: 41 vs 42 us at 4, 80 vs 102 us at 10 steps;
+// 512^2: 41 vs 46 us at 10; 256^2: 32 vs 48 us); below that its block load / store is not amortised.
+constexpr int kResidentMinSteps = 4;
+
 tws_status run_steps(tws_sim* s, int n) {
   const Geom& g = s->geom;
   const bool strip = g.has_up || g.has_down;
@@ -441,6 +448,14 @@ tws_status run_steps(tws_sim* s, int n) {
   TWS_CUDA(s, cudaEventRecord(s->ev_start, s->st_main));
   const int K = s->prm.backend == TWS_BACKEND_RESIDENT ? (1 << 20)
               : (s->prm.backend == TWS_BACKEND_FUSED_TB || is_stream_backend(s->prm.backend)) ? s->K : 1;
+  if (s->res_auto && n >= kResidentMinSteps) {
+    const int keep = s->prm.backend;
+    s->prm.backend = TWS_BACKEND_RESIDENT;
+    const tws_status r = run_block(s, n);
+    s->prm.backend = keep;
+    if (r) return r;
+    n = 0;
+  }
   if (!strip && s->use_graphs && n >= 2 && n <= 64 && s->prm.backend != TWS_BACKEND_RESIDENT) {
     bool done = false;
     tws_status r = run_batch_graph(s, n, K, &done);
@@ -532,6 +547,7 @@ tws_status tws_create(const tws_params* p, tws_sim** out) {
   tws_sim* s = new (std::nothrow) tws_sim;
   if (!s) return fail(nullptr, TWS_ERR_NOMEM, "tws_create: out of host memory");
   s->prm = *p;
+  s->auto_picked = p->backend == TWS_BACKEND_AUTO;
   if (p->backend == TWS_BACKEND_AUTO) {
     // Measured on B200 (scripts/crossover_perf.py, profiles/r01_crossover_tile_vs_band.log): small grids are latency
     // bound and the tile kernel keeps more of the SM busy (209 vs 206 Gcell/s at 3072^2, 177 vs 165 at 2048^2); from
@@ -550,6 +566,12 @@ tws_status tws_create(const tws_params* p, tws_sim** out) {
   g.pitch = pitch_for(p->width);
   g.has_up = p->row_begin > 0; g.has_down = p->row_end < p->height;
   derive_constants(s);
+  if (p->backend == TWS_BACKEND_FUSED_TB && s->auto_picked && !strip) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+    s->res_cfg = resident_config(g);
+    s->res_auto = s->res_cfg >= 0 && 4 * resident_blocks(g, s->res_cfg) >= 3 * sms;     // most SMs get a block
+  }
   if (p->backend == TWS_BACKEND_RESIDENT) {
     s->res_cfg = resident_config(g);
     if (s->res_cfg < 0) {
