@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) scene_kernel(Geom g, float* h, float* d /
     const float terrain = (n * 0.5f + 0.5f) * height_scale;
     const float px = (float)x * mx - 0.5f, py = (float)gy * my - 0.5f;
     const float l2 = px * px + py * py;
-    const float p = l2 * l2;                             // pow(l2, 2.0f), PINNED to the product (oracle/tws_oracle.cpp: g++ folds the
+    const float p = l2 * l2;                             // pow(l2, 2.0f), PINNED to the product (g++ folds the
                                                          // reference generator's own call to this; a library powf may differ in the last bit)
     const float water = (0.45f - p * 800.0f) * height_scale - terrain;
     const long long o = (long long)lr * g.pitch + x;

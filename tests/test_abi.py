@@ -125,7 +125,7 @@ def test_no_fused_multiply_add_in_the_step_kernels(tws):
     sass = subprocess.run([cuobjdump, "-sass", str(LIB_PATH)], capture_output=True, text=True).stdout
     assert "Function :" in sass
     assert "FFMA2" not in sass, "a packed multiply was contracted into a packed FMA"
-    for name, body in re.findall(r"Function : (\S*(?:band_step|fused_step|stream_step|unfused_update|unfused_apply)\S*)(.*?)(?=Function :|\Z)", sass, re.S):
+    for name, body in re.findall(r"Function : (\S*(?:band_step|fused_step|stream_step|resident_step|unfused_update|unfused_apply)\S*)(.*?)(?=Function :|\Z)", sass, re.S):
         n_ffma = len(re.findall(r"\bFFMA\b", body))
         n_rcp = len(re.findall(r"\bMUFU\.RCP\b", body))
         n_call = len(re.findall(r"\bCALL\.REL", body))
