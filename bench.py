@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--verify-strips", action="store_true", help="also compare the strips of the BENCH grid with a whole-grid run on rank 0 (small --size only)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (BASELINE config 4: 32768^2 split over the ranks)")
+    ap.add_argument("--no-frame", action="store_true", help="skip the 1024^2 frame-time sub-record (the reference's own operating point)")
     ap.add_argument("--strong-size", type=int, default=32768)
     ap.add_argument("--strong-steps", type=int, default=48)
     return ap.parse_args()
@@ -260,6 +261,52 @@ def cpu_oracle_throughput(size: int, steps: int, warmup: int, budget_s: float, o
     sample = (f"{size}x{rows} central-row slab of the {size}x{size} reference scene, {steps} steps after {warmup} warm-up, "
               + (f"OpenMP oracle on {cores} threads" if openmp else "single-threaded oracle"))
     return gcells, cores, sample, dt / steps * 1e3
+
+
+def reference_frame_times(tws, device: int):
+    """Device time (CUDA events inside the library, best of 20 after 10 warm-up calls) of one tws_step(n) call on the reference's
+    1024 x 1024 default scene: n = 10 (its per-frame maximum, Terrain.cpp:247) and n = 1, through TWS_BACKEND_AUTO (calls of
+    >= 4 steps run as ONE resident launch), next to the tile kernel's captured batch of the same n; plus the reference's whole
+    frame (brush + one step + full mip chain of TerrainInfo: what its on-screen 'Simulation Time' covers), wall clock."""
+    import ctypes as C
+    out = {"grid": [1024, 1024], "unit": "us", "timing": "device (CUDA events), best of 20 calls"}
+
+    def best(sim, n):
+        for _ in range(10):
+            sim.step(n)
+        sim.sync()
+        b = 1e30
+        for _ in range(20):
+            sim.step(n); sim.sync()
+            b = min(b, sim.elapsed_ms() * 1e3)
+        return b
+
+    with tws.Terrain(1024, device=device) as sim:                       # AUTO
+        sim.CreateHeightmapFromNoiseAndResetSim()
+        l0 = sim.kernel_launches(); sim.step(10); sim.sync()
+        out["frame10_launches"] = int(sim.kernel_launches() - l0)
+        out["frame10_auto"] = best(sim, 10)
+        out["frame1_auto"] = best(sim, 1)
+        lib, h = sim._lib, sim._sim
+        n = C.c_uint32(0); base = C.c_void_p(); lv = C.c_int32(0)
+
+        def frame():
+            lib.tws_inject_brush_world(h, C.c_float(512.0), C.c_float(512.0), C.c_float(100.0 / 60.0))
+            lib.tws_advance(h, C.c_double(1.0 / 60.0 + 1e-9), C.byref(n))
+            lib.tws_publish_mips(h, C.byref(base), C.byref(lv))
+        for _ in range(50):
+            frame()
+        sim.sync()
+        t0 = time.perf_counter()
+        for _ in range(500):
+            frame()
+        sim.sync()
+        out["reference_frame_wall"] = (time.perf_counter() - t0) / 500 * 1e6
+        out["reference_frame"] = "brush + 1 step + %d-level mip chain through the C ABI, wall clock per frame over 500 frames" % lv.value
+    with tws.Terrain(1024, backend=tws.BACKEND_FUSED_TB, temporal_block=2, device=device) as sim:
+        sim.CreateHeightmapFromNoiseAndResetSim()
+        out["frame10_tile_k2"] = best(sim, 10)
+    return out
 
 
 def run_reference(args):
@@ -551,6 +598,14 @@ def run_b200(args):
                       "efficiency": t1_ms / (world * tn_ms),
                       "definition": "T1 / (N x TN), both measured in THIS run: T1 = the whole grid on rank 0's GPU alone, TN = the same grid as N strips, device time, max over ranks (SURVEY 8d)"}
 
+    # ---- the reference's own operating point (BASELINE configs[0/1] grid, Terrain.cpp:240-277): 1024^2, frames of up to 10 steps
+    frame = None
+    if rank == 0 and not args.no_frame:
+        try:
+            frame = reference_frame_times(tws, local)
+        except Exception as e:                          # an extra figure must never cost the bench line
+            frame = {"error": str(e)}
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         val, cores, sample, _ = cpu_oracle_throughput(W, 4, 1, budget_s=20.0)
@@ -568,7 +623,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "per_gpu_value": value / world, "strips_verified": strips_verified, "strong": strong,
+            "per_gpu_value": value / world, "strips_verified": strips_verified, "strong": strong, "frame_1024": frame,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

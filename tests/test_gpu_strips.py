@@ -169,7 +169,7 @@ def test_two_process_ipc(tws, tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(ROOT / "bench.py"), "--gpus", "2", "--steps", "2", "--warmup", "1", "--size", "1024",
-           "--verify-strips", "--no-strong", "--no-cpu-baseline"]
+           "--verify-strips", "--no-strong", "--no-cpu-baseline", "--no-frame"]
     out = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "STRIPS_VERIFIED" in out.stdout
