@@ -399,11 +399,20 @@ int res_sm_count() {
   return cached[dev & 63] > 0 ? cached[dev & 63] : 148;
 }
 
+// Can this device hold every block of the grid at once?  (One CTA per SM: the shared memory opt-in must succeed and the
+// occupancy calculator must grant a block per SM — a MIG slice or a smaller part says no here, not at launch time.)
 template <class C>
 bool res_fits(const Geom& g, int sms, long long* staged) {
   const long long nbx = (g.W + C::OX - 1) / C::OX, nby = (g.Hg + C::OY - 1) / C::OY;
   *staged = (long long)C::PLANE;
-  return nbx * nby <= sms;
+  if (nbx * nby > sms) return false;
+  int dev = 0, coop = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) return false;
+  auto kern = resident_step_kernel<C>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NT, C::SMEM) != cudaSuccess) { cudaGetLastError(); return false; }
+  return (long long)per_sm * sms >= nbx * nby;
 }
 
 template <class C>
