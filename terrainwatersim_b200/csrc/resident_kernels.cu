@@ -362,16 +362,22 @@ __global__ void __launch_bounds__(C::NT, 1) resident_step_kernel(ResPlanes P, Re
     __syncthreads();                                      // the block's depth of step t is complete
 #pragma unroll
     for (int q = 0; q < C::IPT_EARLY; ++q) res_flux_item<C>(st, it_early[q], gx_base, gy_base, g, c, out_acc);
+    // words whose tag is not the step's yet are re-read — all of a thread's stale words per round trip, not one after the other
+    uint32_t spins = 0;
+    for (bool stale = true; stale && !dead;) {
+      stale = false;
 #pragma unroll
-    for (int q = 0; q < WPT; ++q) {
-      if (mo[q] < 0) continue;
-      uint32_t spins = 0;
-      while (((uint32_t)(wa[q] >> 32) != tag || (uint32_t)(wb[q] >> 32) != tag) && !dead) {
-        mail_load2(mbase + mw[q], wa[q], wb[q]);
-        if (++spins > (1u << 21)) { dead = true; atomicExch(error, 1u); }
-      }
-      *reinterpret_cast<float2*>(st + mo[q]) = make_float2(__uint_as_float((uint32_t)wa[q]), __uint_as_float((uint32_t)wb[q]));
+      for (int q = 0; q < WPT; ++q)
+        if (mo[q] >= 0 && ((uint32_t)(wa[q] >> 32) != tag || (uint32_t)(wb[q] >> 32) != tag)) {
+          mail_load2(mbase + mw[q], wa[q], wb[q]);
+          stale = true;
+        }
+      if (stale && ++spins > (1u << 21)) { dead = true; atomicExch(error, 1u); }
     }
+#pragma unroll
+    for (int q = 0; q < WPT; ++q)
+      if (mo[q] >= 0)
+        *reinterpret_cast<float2*>(st + mo[q]) = make_float2(__uint_as_float((uint32_t)wa[q]), __uint_as_float((uint32_t)wb[q]));
     __syncthreads();                                      // the halo of step t + 1 is in shared memory
 #pragma unroll
     for (int q = 0; q < C::IPT_LATE; ++q) res_flux_item<C>(st, it_late[q], gx_base, gy_base, g, c, out_acc);
