@@ -436,8 +436,8 @@ void next_timing_pair(tws_sim* s) {
 }
 
 // Measured (scripts/resident_perf.py, profiles/r02_resident_frames.log): from 4 steps per call on, one resident launch beats
-// the captured batch of tile-kernel launches on grids that fill the SMs (1024^2: 41 vs 42 us at 4, 80 vs 102 us at 10 steps;
-// 512^2: 41 vs 46 us at 10; 256^2: 32 vs 48 us); below that its block load / store is not amortised.
+// the captured batch of tile-kernel launches on grids that fill the SMs (1024^2: 40 vs 42 us at 4, 80 vs 102 us at 10 steps;
+// 512^2: 37 vs 46 us at 10; 256^2: 27 vs 48 us); below that its block load / store is not amortised.
 constexpr int kResidentMinSteps = 4;
 
 tws_status run_steps(tws_sim* s, int n) {
