@@ -624,6 +624,38 @@ def test_resident_backend_frames_of_any_length_match_the_oracle(tws, oracle_omp,
             assert_state_equal(sim, tws, t, f, v, f"resident {W}x{H} {boundary} after a frame of {n}")
 
 
+def test_resident_backend_long_run_equals_the_tile_kernel_at_1024(tws, oracle_omp):
+    """The reference's operating point for a long time: 1024^2 default scene, 300 frames of 10 steps with the brush before every
+    frame (3000 steps, 2700 rim exchanges per block).  The resident kernel and the tile kernel must agree on every bit of depth,
+    flux and flow vector at the end, and both with the oracle after the first 3 frames."""
+    states = {}
+    for name, backend, k in (("resident", tws.BACKEND_RESIDENT, 1), ("tile", tws.BACKEND_FUSED_TB, 2)):
+        with make_sim(tws, 1024, 1024, backend, k) as sim:
+            sim.CreateHeightmapFromNoiseAndResetSim()
+            early = None
+            for frame in range(300):
+                sim.inject_brush(512.0, 512.0, float(np.float32(100.0 / 60.0)), 32.0)
+                sim.step(10)
+                if frame == 2:
+                    early = (sim.readback(tws.FIELD_WATER), sim.readback(tws.FIELD_FLUX), sim.readback(tws.FIELD_VELOCITY))
+            states[name] = (early, sim.readback(tws.FIELD_WATER), sim.readback(tws.FIELD_FLUX), sim.readback(tws.FIELD_VELOCITY),
+                            sim.boundary_outflow_accumulated())
+    t = oracle_omp.create_scene(1024)
+    f, v = np.zeros((1024, 1024, 4), np.float32), np.zeros((1024, 1024, 2), np.float16)
+    c = oracle_omp.derive_consts(1024.0, 1024)
+    for _ in range(3):
+        oracle_omp.brush(t, 512.0, 512.0, float(np.float32(100.0 / 60.0)), 32.0)
+        oracle_omp.step(t, f, v, c, 10)
+    for name in states:
+        e = states[name][0]
+        assert np.array_equal(bits(e[0]), bits(np.ascontiguousarray(t[..., 3]))) and np.array_equal(bits(e[1]), bits(f)) and \
+            np.array_equal(bits(e[2]), bits(v)), f"{name} differs from the oracle after 30 steps"
+    a, b = states["resident"], states["tile"]
+    for i, what in ((1, "depth"), (2, "flux"), (3, "flow vector")):
+        assert np.array_equal(bits(a[i]), bits(b[i])), f"{what} differs after 3000 steps"
+    assert a[4] == pytest.approx(b[4], rel=1e-12)          # fp64 ledgers: same terms, different summation order
+
+
 def test_resident_backend_refuses_what_does_not_fit(tws):
     with pytest.raises(tws.TwsError) as e:
         tws.Terrain(2048, backend=tws.BACKEND_RESIDENT)
