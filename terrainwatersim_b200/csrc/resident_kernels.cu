@@ -8,7 +8,7 @@
 // CTA publishes travels in an 8-byte word together with the number of the step it belongs to (the scheme NCCL calls LL),
 // so a reader polls the data itself and one L2 round trip is the whole hand-off.  (Round 2 first had the rims go through
 // the state planes behind acquire / release flags: publish -> fence -> flag -> poll -> fetch took 4.6 us per step and set the
-// step time on every grid size; %globaltimer traces in DESIGN.md section 8.)  The launch is cooperative: all CTAs are
+// step time on every grid size; %globaltimer traces in DESIGN.md section 4.)  The launch is cooperative: all CTAs are
 // resident by construction, which the polling relies on.
 //
 // A step's passes are ordered so that the exchange overlaps the arithmetic that does not depend on it:
