@@ -266,7 +266,7 @@ def cpu_oracle_throughput(size: int, steps: int, warmup: int, budget_s: float, o
 def reference_frame_times(tws, device: int):
     """Device time (CUDA events inside the library, best of 20 after 10 warm-up calls) of one tws_step(n) call on the reference's
     1024 x 1024 default scene: n = 10 (its per-frame maximum, Terrain.cpp:247) and n = 1, through TWS_BACKEND_AUTO (calls of
-    >= 4 steps run as ONE resident launch), next to the tile kernel's captured batch of the same n; plus the reference's whole
+    >= 3 steps run as ONE resident launch), next to the tile kernel's captured batch of the same n; plus the reference's whole
     frame (brush + one step + full mip chain of TerrainInfo: what its on-screen 'Simulation Time' covers), wall clock."""
     import ctypes as C
     out = {"grid": [1024, 1024], "unit": "us", "timing": "device (CUDA events), best of 20 calls"}

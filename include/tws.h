@@ -49,7 +49,7 @@ typedef enum tws_backend {
                                band kernel with 4 steps per launch from ~12 M cells up, the
                                tile kernel with 2 below (measured crossover ~3072^2 on B200);
                                on whole grids that fit on chip (see TWS_BACKEND_RESIDENT) calls of
-                               4 or more steps run as one resident launch instead;
+                               3 or more steps run as one resident launch instead;
                                `temporal_block` is ignored; see tws_backend_in_use          */
   TWS_BACKEND_UNFUSED = 1,  /* two kernels per step, mirroring the two dispatches of
                                Terrain.cpp:255-264 (in-place, no shared memory)          */

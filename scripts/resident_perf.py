@@ -4,12 +4,13 @@ import sys; sys.path.insert(0, '.')
 import terrainwatersim_b200 as tws
 
 sizes = [int(x) for x in sys.argv[1].split(',')] if len(sys.argv) > 1 else [256, 512, 1024]
+ns = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [1, 2, 4, 10, 20, 40]
 for W in sizes:
     for name, b, k in (("resident", 6, 1), ("tile k=2", 3, 2)):
         with tws.Terrain(W, backend=b, temporal_block=k) as sim:
             sim.CreateHeightmapFromNoiseAndResetSim()
             row = []
-            for n in (1, 2, 4, 10, 20, 40):
+            for n in ns:
                 for _ in range(10): sim.step(n)
                 sim.sync()
                 best = 1e9

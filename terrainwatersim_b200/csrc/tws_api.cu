@@ -435,10 +435,11 @@ void next_timing_pair(tws_sim* s) {
   s->batches_timed += 1;
 }
 
-// Measured (scripts/resident_perf.py, profiles/r02_resident_frames.log): from 4 steps per call on, one resident launch beats
-// the captured batch of tile-kernel launches on grids that fill the SMs (1024^2: 40 vs 42 us at 4, 80 vs 102 us at 10 steps;
-// 512^2: 37 vs 46 us at 10; 256^2: 27 vs 48 us); below that its block load / store is not amortised.
-constexpr int kResidentMinSteps = 4;
+// Measured (scripts/resident_perf.py, profiles/r02_resident_frames.log): from 3 steps per call on, one resident launch matches
+// or beats the captured batch of tile-kernel launches on grids that fill the SMs (1024^2: 33.1 vs 33.7 us at 3, 40 vs 42 at 4,
+// 80 vs 102 at 10 steps; 512^2: 16.7 vs 19.2 at 3, 37 vs 46 at 10; 256^2: 13.3 vs 18.1 at 3, 27 vs 48 at 10); at 1 and 2 steps
+// its block load / store is not amortised (1024^2: 26.9 vs 23.8 us at 2).
+constexpr int kResidentMinSteps = 3;
 
 tws_status run_steps(tws_sim* s, int n) {
   const Geom& g = s->geom;
