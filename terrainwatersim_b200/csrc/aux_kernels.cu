@@ -24,9 +24,8 @@ __global__ void brush_kernel(Geom g, float* d /* local row 0 */, float cx, float
   d[o] = __fadd_rn(d[o], __fmul_rn(s, intensity));
 }
 
-cudaError_t launch_brush(const Geom& g, float* d, float cx, float cy, float intensity, float size_sq, cudaStream_t st, int* launched) {
-  *launched = 0;
-  if (!(size_sq > 0.0f) || !isfinite(cx) || !isfinite(cy)) return cudaSuccess;       // NaN/0 size: reference adds 0*i or NaN; we refuse upstream
+bool brush_bbox(const Geom& g, float cx, float cy, float size_sq, int* px0, int* px1, int* py0, int* py1) {
+  if (!(size_sq > 0.0f) || !isfinite(cx) || !isfinite(cy)) return false;              // NaN/0 size: reference adds 0*i or NaN; we refuse upstream
   const float rad = ceilf(sqrtf(size_sq)) + 1.0f;
   // Box in global texels, clipped to the rows this strip stores (own rows + live halos).
   const double lo_x = floor((double)cx - rad), hi_x = ceil((double)cx + rad);
@@ -34,10 +33,18 @@ cudaError_t launch_brush(const Geom& g, float* d, float cx, float cy, float inte
   const int row_lo = g.row0 - (g.has_up ? TWS_HALO_ROWS : 0), row_hi = g.row0 + g.rows + (g.has_down ? TWS_HALO_ROWS : 0);
   // a box that misses the stored rows / columns entirely adds 0 everywhere, like the reference's whole-grid pass; decided in
   // double BEFORE any cast to int (a finite centre beyond INT_MAX must not reach the casts)
-  if (lo_x > (double)g.W - 1 || hi_x < 0.0 || lo_y > (double)row_hi - 1 || hi_y < (double)row_lo) return cudaSuccess;
+  if (lo_x > (double)g.W - 1 || hi_x < 0.0 || lo_y > (double)row_hi - 1 || hi_y < (double)row_lo) return false;
   const int x0 = (int)fmax(lo_x, 0.0), x1 = (int)fmin(hi_x, (double)g.W - 1);
   const int y0 = (int)fmax(lo_y, (double)row_lo), y1 = (int)fmin(hi_y, (double)row_hi - 1);
-  if (x1 < x0 || y1 < y0) return cudaSuccess;
+  if (x1 < x0 || y1 < y0) return false;
+  *px0 = x0; *px1 = x1; *py0 = y0; *py1 = y1;
+  return true;
+}
+
+cudaError_t launch_brush(const Geom& g, float* d, float cx, float cy, float intensity, float size_sq, cudaStream_t st, int* launched) {
+  *launched = 0;
+  int x0, x1, y0, y1;
+  if (!brush_bbox(g, cx, cy, size_sq, &x0, &x1, &y0, &y1)) return cudaSuccess;
   const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
   dim3 block(16, 16), grid((bw + 15) / 16, (bh + 15) / 16);
   brush_kernel<<<grid, block, 0, st>>>(g, d, cx, cy, intensity, size_sq, x0, y0, bw, bh);

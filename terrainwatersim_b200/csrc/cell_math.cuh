@@ -137,6 +137,25 @@ __device__ __forceinline__ void ledger_acc(double& acc, const StepConsts& c, con
   acc += s * (double)c.area_inv;
 }
 
+// waterBrush.comp:26-31 for the four cells of a float4 group at global (gx0, gy): the same expression as brush_kernel
+// (aux_kernels.cu), applied to the cells inside the brush's bounding box (outside it the brush adds exactly 0).
+__device__ __forceinline__ float4 brush4(float4 d, const int gx0, const int gy, const BrushArgs& br) {
+  if (gy < br.y0 || gy > br.y1 || gx0 > br.x1 || gx0 + 3 < br.x0) return d;
+  float* pd = &d.x;
+  const float ty = br.cy - (float)gy;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = gx0 + i;
+    if (x < br.x0 || x > br.x1) continue;
+    const float tx = br.cx - (float)x;                                                           // :26
+    const float dist = __fdiv_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)), br.size_sq);   // :27
+    float s = 1.0f - dist;                                                                       // :28
+    s = (s < 0.0f) ? 0.0f : ((s > 1.0f) ? 1.0f : s);
+    pd[i] = __fadd_rn(pd[i], __fmul_rn(s, br.intensity));
+  }
+  return d;
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float x, float y) {                  // rg16f store, :52
   const __half2 h = __floats2half2_rn(x, y);
   return *reinterpret_cast<const uint32_t*>(&h);

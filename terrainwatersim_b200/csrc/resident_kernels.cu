@@ -261,7 +261,7 @@ __device__ __forceinline__ void res_depth_item(float* __restrict__ st, const int
 // n steps of the whole grid; state side `src` -> side (src + n) & 1.  Steps are numbered epoch0 + 1 ... epoch0 + n (the tags).
 template <class C>
 __global__ void __launch_bounds__(C::NT, 1) resident_step_kernel(ResPlanes P, ResMail M, Geom g, StepConsts c, int nbx, int src, int n,
-                                                                 uint32_t epoch0, uint32_t* error) {
+                                                                 uint32_t epoch0, uint32_t* error, BrushArgs br) {
   constexpr int SY = C::SY, NG = C::NG, PLANE = C::PLANE, NT = C::NT, WPT = C::WPT;
   extern __shared__ __align__(1024) float st[];
   const int tid = threadIdx.x;
@@ -278,7 +278,9 @@ __global__ void __launch_bounds__(C::NT, 1) resident_step_kernel(ResPlanes P, Re
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     const int o = a * 4;
     st4(st + o, in ? ldcg4(P.h + go) : z);
-    st4(st + PLANE + o, in ? ldcg4(P.d[src] + go) : z);
+    float4 dd = in ? ldcg4(P.d[src] + go) : z;
+    if (br.active && in) dd = brush4(dd, gx0, gy, br);     // a pending brush (waterBrush.comp), folded into the block load
+    st4(st + PLANE + o, dd);
 #pragma unroll
     for (int k = 0; k < 4; ++k) st4(st + (2 + k) * PLANE + o, in ? ldcg4(P.F[src][k] + go) : z);
   }
@@ -423,7 +425,7 @@ bool res_fits(const Geom& g, int sms, long long* staged) {
 
 template <class C>
 cudaError_t res_launch(const Geom& g, const Planes& p, const StepConsts& c, int src, int n, void* mailbox, uint32_t epoch0,
-                       uint32_t* error, cudaStream_t st) {
+                       uint32_t* error, cudaStream_t st, const BrushArgs* brush) {
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -447,7 +449,9 @@ cudaError_t res_launch(const Geom& g, const Planes& p, const StepConsts& c, int 
   int nbx = (g.W + C::OX - 1) / C::OX, nby = (g.Hg + C::OY - 1) / C::OY;
   Geom gg = g;
   StepConsts cc = c;
-  void* args[] = {&P, &M, &gg, &cc, &nbx, &src, &n, &epoch0, &error};
+  BrushArgs br{};
+  if (brush != nullptr) br = *brush;
+  void* args[] = {&P, &M, &gg, &cc, &nbx, &src, &n, &epoch0, &error, &br};
   // cooperative: every CTA of the grid is resident before any of them runs, which the polling of the neighbours relies on
   return cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)(nbx * nby)), dim3(C::NT), args, C::SMEM, st);
 }
@@ -480,10 +484,10 @@ int resident_blocks(const Geom& g, int cfg) {
 size_t resident_mailbox_bytes(const Geom& g) { return (size_t)10 * (size_t)g.pitch * (size_t)g.Hg * sizeof(unsigned long long); }
 
 cudaError_t launch_resident(int cfg, const Geom& g, const Planes& p, const StepConsts& c, int src, int n, void* mailbox,
-                            uint32_t epoch0, uint32_t* error, cudaStream_t st) {
+                            uint32_t epoch0, uint32_t* error, cudaStream_t st, const BrushArgs* brush) {
   if (n <= 0) return cudaSuccess;
   switch (cfg) {
-#define X(I, C) case I: return res_launch<C>(g, p, c, src, n, mailbox, epoch0, error, st);
+#define X(I, C) case I: return res_launch<C>(g, p, c, src, n, mailbox, epoch0, error, st, brush);
     TWS_RES_CONFIGS(X)
 #undef X
     default: return cudaErrorInvalidValue;

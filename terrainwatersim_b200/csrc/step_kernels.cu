@@ -317,7 +317,8 @@ __device__ __forceinline__ void depth_level(float* __restrict__ st, const int (&
 }
 
 template <class C, bool EDGE>
-__device__ __forceinline__ void run_tile(float* st, const TileCtx& tc, const FusedOut& out, const Geom& g, const StepConsts& c, const int tid) {
+__device__ __forceinline__ void run_tile(float* st, const TileCtx& tc, const FusedOut& out, const Geom& g, const StepConsts& c, const int tid,
+                                         const BrushArgs& br) {
   constexpr int K = C::K, NG = C::NG, SX = C::SX, SY = C::SY, PLANE = C::PLANE, NT = C::NT;
   constexpr int ITEMS = NG * (SY - 2);                 // owned items: staged rows 1..SY-2
   constexpr int IPT = (ITEMS + NT - 1) / NT;
@@ -335,6 +336,7 @@ __device__ __forceinline__ void run_tile(float* st, const TileCtx& tc, const Fus
     valid[q] = a < ITEMS;
     o[q] = (NG + (valid[q] ? a : ITEMS - 1)) * 4;      // row 1 starts NG float4 groups into the plane
     h[q] = ld4(sh + o[q]); d[q] = ld4(sd + o[q]);
+    if (br.active) { const int r = o[q] / SX; d[q] = brush4(d[q], tc.sx0 + (o[q] - r * SX), tc.gy0 + r, br); }   // a pending brush, folded in
     fx[q] = ld4(st + 2 * PLANE + o[q]); fy[q] = ld4(st + 3 * PLANE + o[q]);
     fz[q] = ld4(st + 4 * PLANE + o[q]); fw[q] = ld4(st + 5 * PLANE + o[q]);
   }
@@ -343,7 +345,9 @@ __device__ __forceinline__ void run_tile(float* st, const TileCtx& tc, const Fus
     if (valid[q]) st4(sd + o[q], add4(d[q], h[q]));    // each position is read and rewritten by its owner only
   if (tid < 2 * NG) {                                  // staged rows 0 and SY-1 are never owned: H only
     const int oh = (tid < NG ? tid : (SY - 2) * NG + tid) * 4;
-    st4(sd + oh, add4(ld4(sd + oh), ld4(sh + oh)));
+    float4 dh = ld4(sd + oh);
+    if (br.active) { const int r = oh / SX; dh = brush4(dh, tc.sx0 + (oh - r * SX), tc.gy0 + r, br); }
+    st4(sd + oh, add4(dh, ld4(sh + oh)));
   }
   __syncthreads();
 #pragma unroll 1
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(C::NT, 1) fused_step_kernel(const __grid_const
                                                               const __grid_constant__ CUtensorMap tm_f2,
                                                               const __grid_constant__ CUtensorMap tm_f3,
                                                               FusedOut out, Geom g, StepConsts c, int ty0, int tiles_x, int n_tiles,
-                                                              int tma_y_bias) {
+                                                              int tma_y_bias, BrushArgs br) {
   constexpr int OX = C::OX, OY = C::OY, HX = C::HX, HY = C::HY, SX = C::SX, SY = C::SY, PLANE = C::PLANE, STAGE = C::STAGE;
   extern __shared__ __align__(1024) float smem[];
   __shared__ uint64_t full[2];
@@ -413,8 +417,8 @@ __global__ void __launch_bounds__(C::NT, 1) fused_step_kernel(const __grid_const
     // Tiles whose staged window lies fully inside the grid and whose outputs are all owned rows
     // need no exterior masks, no boundary-mode handling and no store guards.
     const bool edge = tc.sx0 < 0 || tc.sx0 + SX > g.W || tc.gy0 < 0 || tc.gy0 + SY > g.Hg || tc.ly0 + HY + OY > g.rows;
-    if (edge) run_tile<C, true>(st, tc, out, g, c, tid);
-    else run_tile<C, false>(st, tc, out, g, c, tid);
+    if (edge) run_tile<C, true>(st, tc, out, g, c, tid, br);
+    else run_tile<C, false>(st, tc, out, g, c, tid, br);
     __syncthreads();                                  // every read of this stage is done
     if (tid == 0 && tile + 2 * stride < n_tiles) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -443,7 +447,7 @@ static int sm_count_of_current_device() {
 
 template <int K>
 static cudaError_t launch_fused_k(const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int ty0,
-                                  int ty1, cudaStream_t st) {
+                                  int ty1, cudaStream_t st, const BrushArgs* brush) {
   using C = typename CfgFor<K>::type;
   static bool attr_set[64] = {};
   int dev = 0;
@@ -467,7 +471,9 @@ static cudaError_t launch_fused_k(const Geom& g, const Planes& p, const TmaSet& 
   const int sms = sm_count_of_current_device();
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);     // one persistent CTA per SM
   const int bias = g.has_up ? TWS_HALO_ROWS : 0;
-  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], tma.m[2], tma.m[3], tma.m[4], tma.m[5], out, g, c, ty0, tiles_x, (int)n_tiles, bias);
+  BrushArgs br{};
+  if (brush != nullptr) br = *brush;
+  kern<<<grid, C::NT, C::SMEM, st>>>(tma.m[0], tma.m[1], tma.m[2], tma.m[3], tma.m[4], tma.m[5], out, g, c, ty0, tiles_x, (int)n_tiles, bias, br);
   return cudaGetLastError();
 }
 
@@ -482,12 +488,12 @@ int fused_out_rows_per_tile(int K) {
 int fused_tile_rows(int K, int rows) { const int oy = fused_out_rows_per_tile(K); return (rows + oy - 1) / oy; }
 
 cudaError_t launch_fused(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c, int ty0,
-                         int ty1, cudaStream_t st) {
+                         int ty1, cudaStream_t st, const BrushArgs* brush) {
   switch (K) {
-    case 1: return launch_fused_k<1>(g, p, tma, src, c, ty0, ty1, st);
-    case 2: return launch_fused_k<2>(g, p, tma, src, c, ty0, ty1, st);
-    case 3: return launch_fused_k<3>(g, p, tma, src, c, ty0, ty1, st);
-    case 4: return launch_fused_k<4>(g, p, tma, src, c, ty0, ty1, st);
+    case 1: return launch_fused_k<1>(g, p, tma, src, c, ty0, ty1, st, brush);
+    case 2: return launch_fused_k<2>(g, p, tma, src, c, ty0, ty1, st, brush);
+    case 3: return launch_fused_k<3>(g, p, tma, src, c, ty0, ty1, st, brush);
+    case 4: return launch_fused_k<4>(g, p, tma, src, c, ty0, ty1, st, brush);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -67,6 +67,10 @@ struct tws_sim {
   bool res_auto = false;             // TWS_BACKEND_AUTO on a grid that fits on chip: frames of >= kResidentMinSteps steps go resident
   uint32_t res_epoch = 0;            // resident backend: steps run so far (the tags of the rim exchange count them)
   void* res_mailbox = nullptr;       // resident backend: the rim exchange's mailbox (device)
+  // A brush injected on a whole grid that runs the tile kernel is not launched at once: the next single-step launch applies it
+  // while loading the depth (the reference's frame — brush, one step, mip chain — is then two launches).  Anything else that
+  // reads or writes the state first materialises it with the ordinary brush kernel (flush_brush).
+  BrushArgs pending_brush{};
   Peer up, down;
   bool connected = false;
   float* white_dev = nullptr;        // 4096-entry noise table
@@ -314,6 +318,18 @@ tws_status run_block_stream(tws_sim* s, int k) {
   return TWS_OK;
 }
 
+// Materialise a pending brush (see tws_sim::pending_brush) with the brush kernel.
+tws_status flush_brush(tws_sim* s) {
+  if (!s->pending_brush.active) return TWS_OK;
+  const BrushArgs b = s->pending_brush;
+  s->pending_brush.active = 0;
+  int launched = 0;
+  TWS_CUDA(s, launch_brush(s->geom, s->planes.d[s->cur] + (size_t)TWS_HALO_ROWS * s->geom.pitch, b.cx, b.cy, b.intensity, b.size_sq, s->st_main,
+                           &launched));
+  s->launches += launched;
+  return TWS_OK;
+}
+
 // One block of k fused steps (or one unfused step) including the strip exchange.
 tws_status run_block(tws_sim* s, int k) {
   const Geom& g = s->geom;
@@ -331,7 +347,10 @@ tws_status run_block(tws_sim* s, int k) {
       TWS_CUDA(s, cudaMalloc(&s->res_mailbox, resident_mailbox_bytes(g)));
       TWS_CUDA(s, cudaMemsetAsync(s->res_mailbox, 0, resident_mailbox_bytes(g), s->st_main));
     }
-    TWS_CUDA(s, launch_resident(s->res_cfg, g, s->planes, s->consts, src, k, s->res_mailbox, s->res_epoch, &s->ctrl->error, s->st_main));
+    const BrushArgs brush = s->pending_brush;           // folded into the block load
+    s->pending_brush.active = 0;
+    TWS_CUDA(s, launch_resident(s->res_cfg, g, s->planes, s->consts, src, k, s->res_mailbox, s->res_epoch, &s->ctrl->error, s->st_main,
+                                brush.active ? &brush : nullptr));
     s->res_epoch += (uint32_t)k;
     s->launches += 1;
     s->cur = (src + k) & 1;
@@ -341,7 +360,9 @@ tws_status run_block(tws_sim* s, int k) {
   if (r) return r;
   const int tiles = fused_tile_rows(k, g.rows);
   if (!strip) {
-    TWS_CUDA(s, launch_fused(k, g, s->planes, s->tma[k][src], src, s->consts, 0, tiles, s->st_main));
+    const BrushArgs brush = s->pending_brush;           // folded into this launch's loads (run_steps flushed it otherwise)
+    s->pending_brush.active = 0;
+    TWS_CUDA(s, launch_fused(k, g, s->planes, s->tma[k][src], src, s->consts, 0, tiles, s->st_main, brush.active ? &brush : nullptr));
     s->launches += 1;
     s->cur = 1 - src;
     return TWS_OK;
@@ -447,6 +468,13 @@ tws_status run_steps(tws_sim* s, int n) {
   if (strip && !s->connected) return fail(s, TWS_ERR_STATE, "strip sim stepped before tws_halo_connect");
   next_timing_pair(s);
   TWS_CUDA(s, cudaEventRecord(s->ev_start, s->st_main));
+  if (s->pending_brush.active && n > 0) {
+    // only a direct tile-kernel or resident launch takes the brush along (captured batches bake their arguments in)
+    const bool tile = s->prm.backend == TWS_BACKEND_FUSED || s->prm.backend == TWS_BACKEND_FUSED_TB;
+    const bool resident = s->prm.backend == TWS_BACKEND_RESIDENT || (s->res_auto && n >= kResidentMinSteps);
+    const bool batch = !resident && s->use_graphs && n >= 2 && n <= 64;
+    if (strip || !(tile || resident) || batch) { tws_status r = flush_brush(s); if (r) return r; }
+  }
   const int K = s->prm.backend == TWS_BACKEND_RESIDENT ? (1 << 20)
               : (s->prm.backend == TWS_BACKEND_FUSED_TB || is_stream_backend(s->prm.backend)) ? s->K : 1;
   if (s->res_auto && n >= kResidentMinSteps) {
@@ -476,6 +504,7 @@ tws_status run_steps(tws_sim* s, int n) {
 }
 
 tws_status sync_all(tws_sim* s) {
+  { tws_status fr = flush_brush(s); if (fr) return fr; }         // whoever synchronises is about to look at the state
   TWS_CUDA(s, cudaStreamSynchronize(s->st_edge));
   TWS_CUDA(s, cudaStreamSynchronize(s->st_main));
   uint32_t e = 0;
@@ -787,6 +816,16 @@ tws_status tws_inject_brush(tws_sim* s, float cx, float cy, float intensity, flo
     TWS_CUDA(s, launch_wait_flags(s->ctrl, s->geom.has_up, s->geom.has_down, s->epoch, s->st_main));
     s->launches += 1;
   }
+  { tws_status fr = flush_brush(s); if (fr) return fr; }          // an earlier brush that is still pending goes first
+  if (!strip && (s->prm.backend == TWS_BACKEND_FUSED || s->prm.backend == TWS_BACKEND_FUSED_TB || s->prm.backend == TWS_BACKEND_RESIDENT)) {
+    // whole grid on the tile or the resident kernel: the next direct launch applies the brush while it loads the depth
+    BrushArgs b{};
+    if (brush_bbox(s->geom, cx, cy, size_sq, &b.x0, &b.x1, &b.y0, &b.y1)) {
+      b.active = 1; b.cx = cx; b.cy = cy; b.intensity = intensity; b.size_sq = size_sq;
+      s->pending_brush = b;
+    }
+    return TWS_OK;
+  }
   int launched = 0;
   TWS_CUDA(s, launch_brush(s->geom, s->planes.d[s->cur] + (size_t)TWS_HALO_ROWS * s->geom.pitch, cx, cy, intensity, size_sq, s->st_main, &launched));
   s->launches += launched;
@@ -822,6 +861,7 @@ tws_status tws_step_host(tws_sim* s, const float* water_in, float* water_out, vo
   const size_t plane_bytes = (size_t)g.W * g.rows * 4;
   const bool strip = g.has_up || g.has_down;
   if (strip && !s->connected) return fail(s, TWS_ERR_STATE, "strip sim stepped before tws_halo_connect");
+  { tws_status fr = flush_brush(s); if (fr) return fr; }
   if (s->prm.backend == TWS_BACKEND_UNFUSED) {
     // The unfused baseline updates in place: no band pipeline.
     tws_status r = TWS_OK;
@@ -1069,6 +1109,11 @@ uint64_t tws_graph_replays(const tws_sim* s) { return s ? s->graph_replays : 0; 
 
 tws_status tws_device_view(tws_sim* s, tws_field field, void** ptr, int64_t* pitch) {
   if (!s || !ptr || !pitch) return TWS_ERR_INVALID;
+  {
+    DeviceGuard guard(s->prm.device);
+    tws_status fr = flush_brush(s);                      // the caller is about to read the planes with its own kernels
+    if (fr) return fr;
+  }
   const size_t off = (size_t)TWS_HALO_ROWS * s->geom.pitch;
   switch (field) {
     case TWS_FIELD_TERRAIN: *ptr = s->planes.h + off; break;
@@ -1191,6 +1236,7 @@ size_t mip_chain_texels(int w, int h) {
 // level 0 of TerrainInfo, the flow map and — with_level1 — mip level 1 into the publish buffers, in one launch; the info
 // buffer has room for the whole chain
 tws_status publish_level0(tws_sim* s, bool with_level1) {
+  { tws_status fr = flush_brush(s); if (fr) return fr; }
   const Geom& g = s->geom;
   const size_t cells = (size_t)g.W * g.rows;
   if (!s->packed_info) TWS_CUDA(s, cudaMalloc(&s->packed_info, mip_chain_texels(g.W, g.rows) * 16));
@@ -1216,6 +1262,7 @@ int strip_mip_levels(const Geom& g) {
 // neighbours (strip_mip_levels; plan_strips cuts on multiples of 8 rows, so at least levels 0-3); the consumer gathers
 // the strips' level L rows and filters the few remaining small levels itself (tws.h).
 tws_status publish_chain(tws_sim* s) {
+  { tws_status fr = flush_brush(s); if (fr) return fr; }
   const Geom& g = s->geom;
   const int L = strip_mip_levels(g);
   if (publish_all_applicable(g, L)) {                   // e.g. the reference's 1024^2: the whole hand-off is one launch

@@ -104,6 +104,17 @@ struct BandEdge {
   float* down[5];
 };
 
+// A brush (waterBrush.comp:20-31) that the next tile-kernel launch applies while it loads the depth — the separate brush
+// launch of the reference's frame (brush, step, mip chain) folded into the step.  [x0, x1] x [y0, y1]: the brush's bounding
+// box in global texels, clipped to the grid; outside it the brush adds exactly 0.
+struct BrushArgs {
+  int active;
+  float cx, cy, intensity, size_sq;
+  int x0, x1, y0, y1;
+};
+// the bounding box launch_brush uses; false: the brush misses the stored rows / columns entirely (adds 0 everywhere)
+bool brush_bbox(const Geom& g, float cx, float cy, float size_sq, int* x0, int* x1, int* y0, int* y1);
+
 // ---- launchers (step_kernels.cu) ------------------------------------------------------
 // Fused K-level step over tile rows [ty0, ty1) of the strip; reads side `src`, writes 1-src.
 // Returns the number of tile rows for the strip through tiles_y when called with ty1 < 0.
@@ -111,7 +122,7 @@ int  fused_tile_rows(int K, int rows);
 int  fused_out_rows_per_tile(int K);
 cudaError_t fused_build_tma(int K, const Geom& g, const Planes& p, int side, TmaSet* out, std::string* err);
 cudaError_t launch_fused(int K, const Geom& g, const Planes& p, const TmaSet& tma, int src, const StepConsts& c,
-                         int ty0, int ty1, cudaStream_t st);
+                         int ty0, int ty1, cudaStream_t st, const BrushArgs* brush = nullptr);
 // Row-streaming pipeline (stream_kernels.cu): K steps over local rows [lr0, lr1) of the strip.
 cudaError_t build_tma_boxes(const Geom& g, const Planes& p, int side, int box_x, int box_y, TmaSet* out, std::string* err,
                             int l2_promotion);   // 0 none, 1 128 B, 2 256 B
@@ -140,7 +151,7 @@ int resident_blocks(const Geom& g, int cfg);
 // epoch0: steps this sim's resident launches have run before (tags must never repeat)
 size_t resident_mailbox_bytes(const Geom& g);
 cudaError_t launch_resident(int cfg, const Geom& g, const Planes& p, const StepConsts& c, int src, int n, void* mailbox,
-                            uint32_t epoch0, uint32_t* error, cudaStream_t st);
+                            uint32_t epoch0, uint32_t* error, cudaStream_t st, const BrushArgs* brush = nullptr);
 
 // ---- launchers (aux_kernels.cu) -------------------------------------------------------
 cudaError_t launch_brush(const Geom& g, float* d, float cx, float cy, float intensity, float size_sq, cudaStream_t st, int* launched);

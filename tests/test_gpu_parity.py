@@ -225,6 +225,53 @@ def test_inject_brush_matches_whole_grid_pass(tws, oracle, cx, cy, inten, size):
         assert np.array_equal(bits(sim.readback(tws.FIELD_WATER)), bits(np.ascontiguousarray(t[..., 3])))
 
 
+@pytest.mark.parametrize("backend,k", [(2, 1), (3, 2), (0, 1), (6, 1)], ids=["fused", "fused_tb2", "auto", "resident"])
+@pytest.mark.parametrize("W,H", [(300, 200), (1024, 1024)])
+def test_brush_is_folded_into_the_next_single_step_launch(tws, oracle_omp, W, H, backend, k):
+    """On a whole grid that runs the tile kernel (or the resident kernel) a brush is not launched on its own: the next direct
+    step launch applies it while loading the depth (the reference's frame — ApplyRadialWaterBrush, one step, GenMipMaps — is two launches).  Same bits as
+    brush-then-step on the oracle for brushes on tile seams, tile corners, the grid's corners and edges, partly and wholly off
+    the grid; anything that looks at the state before the step (a second brush, a readback, the renderer hand-off, a
+    multi-step call) materialises the brush first."""
+    h, d = bumpy(W, H, seed=21)
+    c = oracle_omp.derive_consts(float(W), W)
+    t, f, v = new_state(h, d)
+    spots = [(W * 0.5, H * 0.5, 1.5, 32.0), (128.0, 28.0, 0.7, 32.0), (127.5, 27.5, 0.7, 20.0), (255.9, 55.5, 1.0, 90.0), (0.0, 0.0, 2.0, 32.0),
+             (W - 1.0, H - 1.0, 2.0, 32.0), (-3.0, 5.0, 1.0, 32.0), (W + 2.5, H * 0.5, 1.0, 40.0), (-500.0, -500.0, 1.0, 32.0), (64.0, H - 0.5, -0.25, 32.0)]
+    with make_sim(tws, W, H, backend, k) as sim:
+        sim.upload(tws.FIELD_TERRAIN, h)
+        sim.upload(tws.FIELD_WATER, d)
+        for cx, cy, inten, size in spots:
+            sim.inject_brush(cx, cy, inten, size)
+            l0 = sim.kernel_launches()
+            sim.step(1)
+            assert sim.kernel_launches() - l0 == 1, "the brush took a launch of its own"
+            oracle_omp.brush(t, cx, cy, inten, size)
+            oracle_omp.step(t, f, v, c, 1)
+        assert_state_equal(sim, tws, t, f, v, "brush folded into the step")
+        # two brushes before one step: the first is materialised by the second, the second rides along
+        sim.inject_brush(100.0, 100.0, 1.0, 32.0); sim.inject_brush(103.0, 98.0, 0.5, 50.0)
+        sim.step(1)
+        oracle_omp.brush(t, 100.0, 100.0, 1.0, 32.0); oracle_omp.brush(t, 103.0, 98.0, 0.5, 50.0)
+        oracle_omp.step(t, f, v, c, 1)
+        assert_state_equal(sim, tws, t, f, v, "two brushes, one step")
+        # a brush that is looked at before any step
+        sim.inject_brush(40.0, 60.0, 3.0, 32.0)
+        oracle_omp.brush(t, 40.0, 60.0, 3.0, 32.0)
+        assert np.array_equal(bits(sim.readback(tws.FIELD_WATER)), bits(np.ascontiguousarray(t[..., 3])))
+        # ... before a multi-step call (a captured batch or the resident kernel), and before the renderer hand-off
+        for n in (2, 5):
+            sim.inject_brush(200.0, 30.0, 1.0, 32.0)
+            sim.step(n)
+            oracle_omp.brush(t, 200.0, 30.0, 1.0, 32.0)
+            oracle_omp.step(t, f, v, c, n)
+        sim.inject_brush(10.0, 10.0, 1.0, 32.0)
+        oracle_omp.brush(t, 10.0, 10.0, 1.0, 32.0)
+        level0 = sim.publish_mips()[0]
+        assert np.array_equal(bits(np.ascontiguousarray(level0[..., 3])), bits(np.ascontiguousarray(t[..., 3])))
+        assert_state_equal(sim, tws, t, f, v, "after flushes")
+
+
 def test_reference_interface_frame_loop(tws, oracle):
     """Scene::Update order (Scene.cpp:356-363): brush with strength dt*100 at the camera XZ, then
     PerformSimulationStep(dt) with the accumulator / 10-step clamp of Terrain.cpp:240-247."""
