@@ -172,7 +172,10 @@ tws_status tws_reset_reference_scene_tiled(tws_sim* s, uint32_t seed, float heig
  * tws_inject_brush_world takes the world XZ position like the reference and derives the
  * texel centre (Terrain.cpp:152-155); tws_inject_brush takes the texel-space centre
  * (global coordinates).  Only the brush's bounding box is touched, result identical to
- * the reference's whole-grid pass.  size_sq is 32 in the reference (Terrain.cpp:159). */
+ * the reference's whole-grid pass.  size_sq is 32 in the reference (Terrain.cpp:159).
+ * On a whole grid stepped by the tile or the resident kernel the brush costs no launch of its own: the
+ * next tws_step / tws_advance applies it while loading the depth; every other call that reads or writes
+ * the state applies it first, so it is always as if the brush had run at once. */
 tws_status tws_inject_brush(tws_sim* s, float center_x, float center_y, float intensity, float size_sq);
 tws_status tws_inject_brush_world(tws_sim* s, float world_x, float world_z, float strength);
 
