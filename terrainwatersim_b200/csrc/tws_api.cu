@@ -459,8 +459,13 @@ void next_timing_pair(tws_sim* s) {
 // Measured (scripts/resident_perf.py, profiles/r02_resident_frames.log): from 3 steps per call on, one resident launch matches
 // or beats the captured batch of tile-kernel launches on grids that fill the SMs (1024^2: 33.1 vs 33.7 us at 3, 40 vs 42 at 4,
 // 80 vs 102 at 10 steps; 512^2: 16.7 vs 19.2 at 3, 37 vs 46 at 10; 256^2: 13.3 vs 18.1 at 3, 27 vs 48 at 10); at 1 and 2 steps
-// its block load / store is not amortised (1024^2: 26.9 vs 23.8 us at 2).
+// its block load / store is not amortised (1024^2: 26.9 vs 23.8 us at 2) — except on grids so small that a launch is all
+// latency (256^2: 8.8 vs 11.5 us at 1, 11.0 vs 11.8 at 2).
 constexpr int kResidentMinSteps = 3;
+constexpr long long kResidentAlwaysCells = 100 * 1000;
+inline int resident_min_steps(const tws_sim* s) {
+  return (long long)s->geom.W * s->geom.rows <= kResidentAlwaysCells ? 1 : kResidentMinSteps;
+}
 
 tws_status run_steps(tws_sim* s, int n) {
   const Geom& g = s->geom;
@@ -471,13 +476,13 @@ tws_status run_steps(tws_sim* s, int n) {
   if (s->pending_brush.active && n > 0) {
     // only a direct tile-kernel or resident launch takes the brush along (captured batches bake their arguments in)
     const bool tile = s->prm.backend == TWS_BACKEND_FUSED || s->prm.backend == TWS_BACKEND_FUSED_TB;
-    const bool resident = s->prm.backend == TWS_BACKEND_RESIDENT || (s->res_auto && n >= kResidentMinSteps);
+    const bool resident = s->prm.backend == TWS_BACKEND_RESIDENT || (s->res_auto && n >= resident_min_steps(s));
     const bool batch = !resident && s->use_graphs && n >= 2 && n <= 64;
     if (strip || !(tile || resident) || batch) { tws_status r = flush_brush(s); if (r) return r; }
   }
   const int K = s->prm.backend == TWS_BACKEND_RESIDENT ? (1 << 20)
               : (s->prm.backend == TWS_BACKEND_FUSED_TB || is_stream_backend(s->prm.backend)) ? s->K : 1;
-  if (s->res_auto && n >= kResidentMinSteps) {
+  if (s->res_auto && n >= resident_min_steps(s)) {
     const int keep = s->prm.backend;
     s->prm.backend = TWS_BACKEND_RESIDENT;
     const tws_status r = run_block(s, n);
