@@ -9,6 +9,7 @@
 #   launches [bench.py args]   ncu launch list (gpu__time_duration.sum) of a short bench command
 #   ncu <regex> <backend> <k> <tag>    ncu --set full of one launch (scripts/stream_check.py as the driver)
 #   py <script.py> [args]      run a Python script from scripts/
+#   refframe [frames]          the reference's frame timed from C++ through include/tws_terrain.hpp (scripts/refframe.cpp)
 set -u
 mkdir -p gpurun_out
 job=${1:-tests}; shift || true
@@ -37,6 +38,10 @@ case "$job" in
   ncu)
     ncu --set full --clock-control none --import-source on -k regex:$1 -s 3 -c 1 -f -o gpurun_out/prof_$4 python scripts/stream_check.py $2 $3 --no-parity > gpurun_out/ncu_$4.log 2>&1
     tail -n 2 gpurun_out/ncu_$4.log ;;
+  refframe)
+    mkdir -p build
+    g++ -O2 -std=c++17 -Iinclude scripts/refframe.cpp -o build/refframe -Lterrainwatersim_b200 -ltws -Wl,-rpath,$PWD/terrainwatersim_b200 \
+      && ./build/refframe ${1:-3000} | tee gpurun_out/refframe.log ;;
   py)
     s=$1; shift
     timeout 1500 python scripts/$s "$@" 2>&1 | tee gpurun_out/${s%.py}.log | tail -40 ;;
